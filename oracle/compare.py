@@ -1,0 +1,30 @@
+"""ORACLE helper (test infrastructure): tolerant comparison for the view-synthesis path.
+
+The path contains two discrete decisions whose outcome can flip under last-ulp differences of fp32
+arithmetic (SURVEY.md section 7 "bit-level habits"): the per-pixel argmin over candidate losses
+(Trainer.py:347) and the floor() of the sampling coordinate (Trainer.py:281).  A flip changes a 3x3
+(SSIM window) patch of per-pixel gradients discontinuously, so per-pixel comparisons allow a small
+fraction of outliers while integrated quantities (losses, pose gradients, L2 norms) stay tight.
+"""
+import torch
+
+
+def robust_report(got, ref, rtol=1e-4):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    scale = ref.abs().max().item() + 1e-30
+    d = (got - ref).abs()
+    return {
+        "max_err": d.max().item(),
+        "scale": scale,
+        "outlier_frac": (d > rtol * scale).double().mean().item(),
+        "rel_l2": ((got - ref).norm() / (ref.norm() + 1e-30)).item(),
+    }
+
+
+def assert_close_robust(got, ref, rtol=1e-4, max_outlier_frac=2e-3, max_rel_l2=2e-2, what=""):
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    r = robust_report(got, ref, rtol)
+    assert r["outlier_frac"] <= max_outlier_frac, (what, r)
+    assert r["rel_l2"] <= max_rel_l2, (what, r)
+    return r
