@@ -1,0 +1,377 @@
+// Fused view synthesis + photometric loss, forward (dd_warp_photo_fwd).
+//
+// One CTA owns a 32x32 tile of one image and walks every pyramid level and source frame:
+//   stage A  per halo pixel (34x34, ReflectionPad2d(1) folded into the index map): bilinear
+//            up-sample of disp_s (and flow_s / mask_s), disp->depth, back-projection, rigid or
+//            scene-flow transform, projection, border-clamped bilinear gather of the source frame
+//            -> warped colour tile in shared memory (target tile staged once per CTA);
+//   stage B  3x3 SSIM statistics by a register ring marching down each column (horizontal taps
+//            from shared memory), L1, 0.85/0.15 mix, per-pixel min over {identity, warped}
+//            candidates, block reduction of the selected loss;
+//   stage C  (scene-flow phases) 2^s-block centre averages of the residual flow and of
+//            sample_ego - sample_complete -> c_consistency sum and disp_mag map.
+// HBM traffic per image and level: target + 2 sources once (colours of other levels hit L2),
+// disp_s once; nothing full-resolution is written unless an aux output is requested.
+#include "warp_photo.cuh"
+
+namespace dd {
+
+constexpr int HALO1 = TILE + 2;   // 34
+constexpr int PITCH1 = 36;
+constexpr int PLANE1 = HALO1 * PITCH1;
+
+struct FwdArgs {
+  dd_warp_desc d;
+  dd_warp_aux aux;
+  float* partial;   // [num_scales*DD_NSUM][num_ctas]
+  float min_disp, disp_range;
+  int has_aux;
+};
+
+// shared memory carve-up (floats): Y[3][34][36] | X[2][3][34][36] | side[2][5][32][32] (flow modes)
+__device__ __forceinline__ float* smem_Y(float* s) { return s; }
+__device__ __forceinline__ float* smem_X(float* s, int f) { return s + 3 * PLANE1 * (1 + f); }
+__device__ __forceinline__ float* smem_side(float* s) { return s + 9 * PLANE1; }
+
+struct SsimOut {
+  float L[2][4];   // per frame, per row of the thread's 4-row run
+};
+
+// Stage B: thread = (column lane, 4-row run).  Returns the mixed reprojection loss
+// ssim_w*mean_c(SSIM) + l1_w*mean_c|y-x| (Trainer.py:413-423, tools.py:243-257) per frame.
+template <int F>
+__device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const float* __restrict__ X0,
+                                            const float* __restrict__ X1, int lane, int row0, float ssim_w,
+                                            float l1_w, SsimOut& out) {
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  float ssim_acc[2][4], l1_acc[2][4];
+#pragma unroll
+  for (int f = 0; f < 2; ++f)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ssim_acc[f][k] = 0.f, l1_acc[f][k] = 0.f;
+
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float* Yc = Y + ch * PLANE1;
+    float ay = 0.f, by = 0.f, ayy = 0.f, byy = 0.f;
+    float ax[2] = {0.f, 0.f}, bx[2] = {0.f, 0.f}, axx[2] = {0.f, 0.f}, bxx[2] = {0.f, 0.f}, axy[2] = {0.f, 0.f},
+          bxy[2] = {0.f, 0.f};
+    float yc_prev = 0.f, xc_prev[2] = {0.f, 0.f};
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr) {
+      const int o = (row0 + rr) * PITCH1 + lane;
+      const float yl = Yc[o], yc = Yc[o + 1], yr = Yc[o + 2];
+      const float hy = yl + yc + yr;
+      const float hyy = yl * yl + yc * yc + yr * yr;
+      float hx[2], hxx[2], hxy[2], xcen[2];
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const float* Xc = (f == 0 ? X0 : X1) + ch * PLANE1;
+        const float xl = Xc[o], xc = Xc[o + 1], xr = Xc[o + 2];
+        hx[f] = xl + xc + xr;
+        hxx[f] = xl * xl + xc * xc + xr * xr;
+        hxy[f] = xl * yl + xc * yc + xr * yr;
+        xcen[f] = xc;
+      }
+      if (rr >= 2) {
+        const int k = rr - 2;   // output row row0+k, centre halo row row0+k+1 == previous iteration
+        const float mu_y = (ay + hy) / 9.f;
+        const float e_yy = (ayy + hyy) / 9.f;
+        const float sig_y = e_yy - mu_y * mu_y;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float mu_x = (ax[f] + hx[f]) / 9.f;
+          const float sig_x = (axx[f] + hxx[f]) / 9.f - mu_x * mu_x;
+          const float sig_xy = (axy[f] + hxy[f]) / 9.f - mu_x * mu_y;
+          const float n = (2.f * mu_x * mu_y + C1) * (2.f * sig_xy + C2);
+          const float dn = (mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2);
+          const float s = fminf(fmaxf((1.f - n / dn) / 2.f, 0.f), 1.f);
+          ssim_acc[f][k] += s;
+          l1_acc[f][k] += fabsf(yc_prev - xc_prev[f]);
+        }
+      }
+      ay = by + hy, by = hy, ayy = byy + hyy, byy = hyy;
+      yc_prev = yc;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        ax[f] = bx[f] + hx[f], bx[f] = hx[f];
+        axx[f] = bxx[f] + hxx[f], bxx[f] = hxx[f];
+        axy[f] = bxy[f] + hxy[f], bxy[f] = hxy[f];
+        xc_prev[f] = xcen[f];
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < F; ++f)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out.L[f][k] = ssim_w * (ssim_acc[f][k] / 3.f) + l1_w * (l1_acc[f][k] / 3.f);
+}
+
+template <int MODE, int F>
+__global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_fwd_kernel(const __grid_constant__ FwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ CamConst cam;
+  __shared__ float red[WP_THREADS / 32][8];
+
+  const dd_warp_desc& d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * TILE, c0 = blockIdx.x * TILE;
+  const int H = d.H, W = d.W;
+  const size_t P = (size_t)H * W;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int num_ctas = gridDim.x * gridDim.y * gridDim.z;
+  const bool automask = (d.flags & DD_FLAG_AUTOMASK) != 0;
+
+  load_cam(&cam, d, b, tid);
+
+  float* Y = smem_Y(smem);
+  // ---- target tile (+ identity source tiles) ------------------------------------------------
+  const float* tgt = d.target + (size_t)b * 3 * P;
+  for (int i = tid; i < HALO1 * HALO1; i += WP_THREADS) {
+    const int hr = i / HALO1, hc = i - hr * HALO1;
+    const int r = reflect1(r0 - 1 + hr, H), c = reflect1(c0 - 1 + hc, W);
+    const size_t o = (size_t)r * W + c;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) Y[ch * PLANE1 + hr * PITCH1 + hc] = __ldg(tgt + ch * P + o);
+    if (automask) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const float* src = d.source[f] + (size_t)b * 3 * P;
+        float* X = smem_X(smem, f);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) X[ch * PLANE1 + hr * PITCH1 + hc] = __ldg(src + ch * P + o);
+      }
+    }
+  }
+  __syncthreads();
+
+  const float l1_w = 1.f - d.ssim_weight;
+  SsimOut ident;
+  if (automask) {   // identity reprojection losses (Trainer.py:327-333), level independent
+    ssim_l1_run<F>(Y, smem_X(smem, 0), smem_X(smem, 1), lane, warp * 4, d.ssim_weight, l1_w, ident);
+    __syncthreads();
+  }
+
+  for (int si = 0; si < d.num_scales; ++si) {
+    const int shift = d.scale[si];
+    const int h = H >> shift, w = W >> shift;
+    const size_t p_lo = (size_t)h * w;
+    const float* disp = d.disp[si] + (size_t)b * p_lo;
+
+    // ---- stage A: warp every halo pixel of both frames ---------------------------------------
+    for (int i = tid; i < HALO1 * HALO1; i += WP_THREADS) {
+      const int hr = i / HALO1, hc = i - hr * HALO1;
+      const bool interior = (hr >= 1) && (hr <= TILE) && (hc >= 1) && (hc <= TILE);
+      const int r = reflect1(r0 - 1 + hr, H), c = reflect1(c0 - 1 + hc, W);
+      const Taps ty = up_taps(r, shift, h), tx = up_taps(c, shift, w);
+      PixelGeom pg;
+      {
+        const float du = bilerp(disp, w, ty, tx);                      // Trainer.py:225
+        pg.depth = 1.f / (a.min_disp + a.disp_range * du);               // tools.py:291-298
+        const float u = (float)c, v = (float)r;
+        pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
+                  cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};            // tools.py:193
+        pg.Pc = {pg.depth * pg.ray.x, pg.depth * pg.ray.y, pg.depth * pg.ray.z};   // tools.py:194
+      }
+      const size_t o = (size_t)r * W + c;
+      if (interior && a.has_aux && a.aux.depth[si]) a.aux.depth[si][(size_t)b * P + o] = pg.depth;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        Vec3 cf = {0.f, 0.f, 0.f};
+        float m = 1.f;
+        if (MODE >= 1) {
+          const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo;
+          const float tsv = cam.ts[f];
+          cf = {bilerp(fl, w, ty, tx) * tsv, bilerp(fl + p_lo, w, ty, tx) * tsv,
+                bilerp(fl + 2 * p_lo, w, ty, tx) * tsv};               // Trainer.py:251
+          if (MODE == 2) m = bilerp(d.mask[si][f] + (size_t)b * p_lo, w, ty, tx);   // Trainer.py:242
+        }
+        FrameGeom g;
+        frame_geometry<MODE>(g, pg, &cam, f, cf, m, H, W, interior);
+        const Foot ft = footprint(unnormalise(g.gx, W), unnormalise(g.gy, H), H, W);
+        const float* src = d.source[f] + (size_t)b * 3 * P;
+        float* X = smem_X(smem, f);
+        float col[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          col[ch] = sample_plane(src + ch * P, W, ft);                  // Trainer.py:281
+          X[ch * PLANE1 + hr * PITCH1 + hc] = col[ch];
+        }
+        if (interior) {
+          if (MODE >= 1) {
+            float* side = smem_side(smem) + f * 5 * TILE * TILE + (hr - 1) * TILE + (hc - 1);
+            side[0] = g.res.x, side[TILE * TILE] = g.res.y, side[2 * TILE * TILE] = g.res.z;
+            side[3 * TILE * TILE] = g.dsx, side[4 * TILE * TILE] = g.dsy;
+          }
+          if (a.has_aux) {
+            if (a.aux.warped[si][f]) {
+              float* wout = a.aux.warped[si][f] + (size_t)b * 3 * P + o;
+              wout[0] = col[0], wout[P] = col[1], wout[2 * P] = col[2];
+            }
+            if (a.aux.sample[si][f])
+              reinterpret_cast<float2*>(a.aux.sample[si][f])[(size_t)b * P + o] = make_float2(g.gx, g.gy);
+            if (MODE >= 1 && a.aux.independ[si][f]) {
+              float* io = a.aux.independ[si][f] + (size_t)b * 3 * P + o;
+              io[0] = g.res.x * m, io[P] = g.res.y * m, io[2 * P] = g.res.z * m;   // Trainer.py:253
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stage B: SSIM + L1 + min selection ---------------------------------------------------
+    float s_photo = 0.f, s_ident = 0.f;
+    {
+      SsimOut wl;
+      ssim_l1_run<F>(Y, smem_X(smem, 0), smem_X(smem, 1), lane, warp * 4, d.ssim_weight, l1_w, wl);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + warp * 4 + k, c = c0 + lane;
+        const size_t o = (size_t)r * W + c;
+        float best = 0.f;
+        int arg = 0;
+        bool first = true;
+        if (automask) {   // candidates: identity frames first (Trainer.py:339-347)
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float v = ident.L[f][k];
+            if (d.noise[si]) v += __ldg(d.noise[si] + ((size_t)b * F + f) * P + o) * 0.00001f;
+            if (first || v < best) best = v, arg = f, first = false;
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float v = wl.L[f][k];
+          if (first || v < best) best = v, arg = (automask ? F : 0) + f, first = false;
+        }
+        s_photo += best;
+        const float sel = (automask && arg > F - 1) ? 1.f : 0.f;   // Trainer.py:350
+        s_ident += sel;
+        if (automask && a.has_aux && a.aux.ident_sel[si]) a.aux.ident_sel[si][(size_t)b * P + o] = sel;
+      }
+    }
+
+    // ---- stage C: low-resolution by-products of the scene-flow phases --------------------------
+    float s_cc[2] = {0.f, 0.f}, s_mag[2] = {0.f, 0.f};
+    if (MODE >= 1) {
+      const int tl = TILE >> shift;                    // low-res pixels per tile side
+      const int nc = shift == 0 ? 1 : 2;               // centre taps per axis (bilinear down-sampling)
+      const int off = shift == 0 ? 0 : (1 << (shift - 1)) - 1;
+      const float wgt = shift == 0 ? 1.f : 0.25f;
+      for (int i = tid; i < tl * tl; i += WP_THREADS) {
+        const int li = i / tl, lj = i - li * tl;
+        const int gi = (r0 >> shift) + li, gj = (c0 >> shift) + lj;
+        const size_t ol = (size_t)gi * w + gj;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float* side = smem_side(smem) + f * 5 * TILE * TILE;
+          float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int dy = 0; dy < nc; ++dy)
+            for (int dx = 0; dx < nc; ++dx) {
+              const int q = ((li << shift) + off + dy) * TILE + (lj << shift) + off + dx;
+#pragma unroll
+              for (int k = 0; k < 5; ++k) acc[k] += side[k * TILE * TILE + q];
+            }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) acc[k] *= wgt;   // utils.interp down-sampling (Trainer.py:284,394-395)
+          const float mag = acc[3] * acc[3] + acc[4] * acc[4];          // Trainer.py:396
+          s_mag[f] += mag;
+          if (a.has_aux && a.aux.mag[si][f]) a.aux.mag[si][f][(size_t)b * p_lo + ol] = mag;
+          if (a.has_aux && a.aux.resid[si][f]) {
+            float* ro = a.aux.resid[si][f] + (size_t)b * 3 * p_lo + ol;
+            ro[0] = acc[0], ro[p_lo] = acc[1], ro[2 * p_lo] = acc[2];
+          }
+          if (MODE == 2) {   // c_consistency (Trainer.py:384-386)
+            const float valid = __ldg(disp + ol) > d.mask_disp_thrd ? 1.f : 0.f;
+            const float ms = __ldg(d.mask[si][f] + (size_t)b * p_lo + ol);
+            s_cc[f] += valid * (1.f - ms) * (fabsf(acc[0]) + fabsf(acc[1]) + fabsf(acc[2]));
+          }
+        }
+      }
+    }
+
+    // ---- block reduction of this level's sums -------------------------------------------------
+    float vals[6] = {s_photo, s_cc[0], s_cc[1], s_mag[0], s_mag[1], s_ident};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float v = warp_sum(vals[k]);
+      if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();   // also guards the X tiles / side buffers before the next level overwrites them
+    if (tid < 6) {
+      float v = 0.f;
+#pragma unroll
+      for (int wi = 0; wi < WP_THREADS / 32; ++wi) v += red[wi][tid];
+      a.partial[(size_t)(si * DD_NSUM + tid) * num_ctas + cta] = v;
+    }
+  }
+}
+
+// Deterministic second stage: sums[k] = sum over CTAs of partial[k][cta] (double accumulation).
+__global__ void finalize_sums_kernel(const float* __restrict__ partial, float* __restrict__ sums, int num_ctas,
+                                     int nsum_used) {
+  __shared__ double sh[256 / 32];
+  const int k = blockIdx.x;   // scale*DD_NSUM + slot
+  double acc = 0.0;
+  if ((k % DD_NSUM) < nsum_used)
+    for (int i = threadIdx.x; i < num_ctas; i += blockDim.x) acc += (double)partial[(size_t)k * num_ctas + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    sums[k] = (float)t;
+  }
+}
+
+int validate_desc(const dd_warp_desc* d);   // warp_photo_api.cu
+
+template <int MODE, int F>
+static int launch_fwd(const FwdArgs& args, dim3 grid, size_t smem_bytes, cudaStream_t st) {
+  auto kern = warp_photo_fwd_kernel<MODE, F>;
+  DD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  kern<<<grid, WP_THREADS, smem_bytes, st>>>(args);
+  DD_CHECK_CUDA(cudaGetLastError());
+  return DD_OK;
+}
+
+int warp_photo_fwd_impl(const dd_warp_desc* desc, const dd_warp_aux* aux, float* sums, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st) {
+  int rc = validate_desc(desc);
+  if (rc != DD_OK) return rc;
+  DD_REQUIRE(sums != nullptr, "dd_warp_photo_fwd: sums is NULL");
+  const size_t need = dd_warp_photo_workspace_bytes(desc);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("dd_warp_photo_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DD_ERR_WORKSPACE;
+  }
+  FwdArgs args;
+  args.d = *desc;
+  args.has_aux = aux != nullptr;
+  if (aux) args.aux = *aux; else memset(&args.aux, 0, sizeof(args.aux));
+  args.partial = reinterpret_cast<float*>(workspace);
+  args.min_disp = 1.f / desc->max_depth;
+  args.disp_range = 1.f / desc->min_depth - 1.f / desc->max_depth;
+  const dim3 grid(desc->W / TILE, desc->H / TILE, desc->B);
+  const int num_ctas = grid.x * grid.y * grid.z;
+  const int mode = (desc->flags & DD_FLAG_CMPFLOW) ? ((desc->flags & DD_FLAG_MOTMASK) ? 2 : 1) : 0;
+  size_t smem_bytes = 9 * PLANE1 * sizeof(float);
+  if (mode >= 1) smem_bytes += 2 * 5 * TILE * TILE * sizeof(float);
+  const int F = desc->num_frames;
+  if (mode == 0 && F == 2) rc = launch_fwd<0, 2>(args, grid, smem_bytes, st);
+  else if (mode == 1 && F == 2) rc = launch_fwd<1, 2>(args, grid, smem_bytes, st);
+  else if (mode == 2 && F == 2) rc = launch_fwd<2, 2>(args, grid, smem_bytes, st);
+  else if (mode == 0 && F == 1) rc = launch_fwd<0, 1>(args, grid, smem_bytes, st);
+  else if (mode == 1 && F == 1) rc = launch_fwd<1, 1>(args, grid, smem_bytes, st);
+  else rc = launch_fwd<2, 1>(args, grid, smem_bytes, st);
+  if (rc != DD_OK) return rc;
+  finalize_sums_kernel<<<desc->num_scales * DD_NSUM, 256, 0, st>>>(args.partial, sums, num_ctas, 6);
+  DD_CHECK_CUDA(cudaGetLastError());
+  return DD_OK;
+}
+
+}  // namespace dd
