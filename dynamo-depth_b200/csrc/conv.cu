@@ -1,0 +1,649 @@
+// Fused decoder convolutions: forward, data gradient, weight gradient (fp32 SIMT implicit GEMM).
+//
+//   out = act( conv_k( pad( concat( up(x0), x1 ) ) ) + bias ) [+ residual]
+//
+// The "virtual input" (up-sampling, skip concatenation, reflection / zero padding) is never
+// materialised: the tile loader evaluates it while staging shared memory (layers.py:85-121,
+// depth_decoder.py:46-53,103-113, motion_decoder.py:34-62).  One CTA = 128 threads computes an
+// 8x16 pixel tile for 8*CPT output channels; every thread owns CPT channels x 8 consecutive pixels.
+// The data gradient reuses the same core on the (zero-extended) output gradient with flipped,
+// transposed weights, producing the gradient on the padded grid; a light routing kernel then folds
+// the reflection border back and transposes the up-sampling / concatenation.
+#include <string.h>
+
+#include "dd_common.cuh"
+
+namespace dd {
+
+constexpr int CT_H = 8, CT_W = 16;
+constexpr int CI_T = 8;
+constexpr int IN_PITCH = 20;
+constexpr int IN_PLANE = (CT_H + 2) * IN_PITCH + 4;   // 204: staggers channel planes across banks
+constexpr int CONV_THREADS = 128;
+
+struct VirtIn {
+  const float* x0;
+  const float* x1;
+  int C0, C1, H0, W0, up0;
+  int Hin, Win;
+  int pad_mode;
+};
+
+__device__ __forceinline__ float virt_load(const VirtIn& v, int b, int ci, int y, int x) {
+  if (y < -1 || y > v.Hin || x < -1 || x > v.Win) return 0.f;   // outside even the padded grid (tile overhang)
+  if (v.pad_mode == DD_PAD_REFLECT) {
+    y = reflect1(y, v.Hin);
+    x = reflect1(x, v.Win);
+  } else if (y < 0 || y >= v.Hin || x < 0 || x >= v.Win) {
+    return 0.f;
+  }
+  if (ci < v.C0) {
+    const float* p = v.x0 + ((size_t)b * v.C0 + ci) * v.H0 * v.W0;
+    if (v.up0 == DD_UP_NONE) return __ldg(p + y * v.W0 + x);
+    if (v.up0 == DD_UP_NEAREST2) return __ldg(p + (y >> 1) * v.W0 + (x >> 1));   // F.interpolate nearest (layers.py:121)
+    const Taps ty = up_taps(y, 1, v.H0), tx = up_taps(x, 1, v.W0);               // bilinear x2 (depth_decoder.py:104)
+    return bilerp(p, v.W0, ty, tx);
+  }
+  return __ldg(v.x1 + (((size_t)b * v.C1 + (ci - v.C0)) * v.Hin + y) * v.Win + x);
+}
+
+struct ConvArgs {
+  VirtIn vin;
+  int B, Ho, Wo;    // output grid
+  int oy, ox;       // virtual-input coordinate of the centre tap of output (0,0)
+  int Cin, Cout;
+  const float* wt;  // prepared weights [Cin][k*k][cout_pad]
+  int cout_pad;
+  const float* bias;
+  const float* residual;
+  int act;
+  float* out;
+  int tiles_x;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == DD_ACT_ELU) return v > 0.f ? v : expf(v) - 1.f;   // nn.ELU(alpha=1) (layers.py:92)
+  if (act == DD_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  if (act == DD_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+template <int KS, int CPT>
+__global__ void __launch_bounds__(CONV_THREADS) conv_core_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int KK = KS * KS;
+  constexpr int HALO = KS / 2;
+  constexpr int ROWS = CT_H + 2 * HALO, COLS = CT_W + 2 * HALO;
+  constexpr int CO_T = 8 * CPT;
+  constexpr int NV = 8 + KS - 1;
+  __shared__ __align__(16) float in_s[CI_T * IN_PLANE];
+  __shared__ __align__(16) float w_s[CI_T * KK * CO_T];
+
+  const int tid = threadIdx.x;
+  const int pg = tid & 15, cg = tid >> 4;
+  const int row = pg & 7, seg = pg >> 3;
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / a.tiles_x) * CT_H, tx0 = (tile % a.tiles_x) * CT_W;
+  const int co0 = blockIdx.y * CO_T;
+  const int b = blockIdx.z;
+
+  float acc[CPT][8];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c)
+#pragma unroll
+    for (int p = 0; p < 8; ++p) acc[c][p] = 0.f;
+
+  for (int ci0 = 0; ci0 < a.Cin; ci0 += CI_T) {
+    // stage the virtual-input tile
+    for (int i = tid; i < CI_T * ROWS * COLS; i += CONV_THREADS) {
+      const int ci = i / (ROWS * COLS);
+      const int rem = i - ci * (ROWS * COLS);
+      const int r = rem / COLS, c = rem - r * COLS;
+      float v = 0.f;
+      if (ci0 + ci < a.Cin) v = virt_load(a.vin, b, ci0 + ci, ty0 + r - HALO + a.oy, tx0 + c - HALO + a.ox);
+      in_s[ci * IN_PLANE + r * IN_PITCH + c] = v;
+    }
+    // stage the weights [ci][tap][co]
+    for (int i = tid; i < CI_T * KK * (CO_T / 4 > 0 ? CO_T / 4 : 1); i += CONV_THREADS) {
+      const int per = CO_T / 4;
+      const int q = i % per, ct = i / per;   // ct = ci*KK + tap
+      const int ci = ct / KK;
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ci0 + ci < a.Cin)
+        w4 = __ldg(reinterpret_cast<const float4*>(a.wt + ((size_t)(ci0 * KK + ct)) * a.cout_pad + co0 + q * 4));
+      reinterpret_cast<float4*>(w_s)[ct * per + q] = w4;
+    }
+    __syncthreads();
+
+#pragma unroll 2
+    for (int ci = 0; ci < CI_T; ++ci) {
+      const float* ip = in_s + ci * IN_PLANE + row * IN_PITCH + seg * 8;
+      float iv[KS][NV];
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy) {
+        const float4 v0 = *reinterpret_cast<const float4*>(ip + dy * IN_PITCH);
+        const float4 v1 = *reinterpret_cast<const float4*>(ip + dy * IN_PITCH + 4);
+        iv[dy][0] = v0.x, iv[dy][1] = v0.y, iv[dy][2] = v0.z, iv[dy][3] = v0.w;
+        iv[dy][4] = v1.x, iv[dy][5] = v1.y, iv[dy][6] = v1.z, iv[dy][7] = v1.w;
+        if (KS == 3) {
+          const float2 v2 = *reinterpret_cast<const float2*>(ip + dy * IN_PITCH + 8);
+          iv[dy][NV - 2] = v2.x, iv[dy][NV - 1] = v2.y;
+        }
+      }
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx) {
+          const float* wp = w_s + (ci * KK + dy * KS + dx) * CO_T + cg * CPT;
+          float wv[CPT];
+          if (CPT >= 4) {
+#pragma unroll
+            for (int q = 0; q < CPT / 4; ++q) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wp + q * 4);
+              wv[q * 4 + 0] = w4.x, wv[q * 4 + 1] = w4.y, wv[q * 4 + 2] = w4.z, wv[q * 4 + 3] = w4.w;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) wv[c] = wp[c];
+          }
+#pragma unroll
+          for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int p = 0; p < 8; ++p) acc[c][p] = fmaf(wv[c], iv[dy][p + dx], acc[c][p]);
+        }
+    }
+    __syncthreads();
+  }
+
+  // epilogue: bias, activation, residual, store
+  const int y = ty0 + row;
+  const int xb = tx0 + seg * 8;
+  if (y >= a.Ho) return;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int co = co0 + cg * CPT + c;
+    if (co >= a.Cout) continue;
+    const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+    const size_t o = (((size_t)b * a.Cout + co) * a.Ho + y) * a.Wo + xb;
+    float v[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      v[p] = apply_act(acc[c][p] + bv, a.act);
+      if (a.residual && xb + p < a.Wo) v[p] += __ldg(a.residual + o + p);
+    }
+    if (xb + 7 < a.Wo && (a.Wo & 3) == 0) {
+      reinterpret_cast<float4*>(a.out + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(a.out + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if (xb + p < a.Wo) a.out[o + p] = v[p];
+    }
+  }
+}
+
+// wt[ci][tap][co] (zero padded to cout_pad) from OIHW weights; `transpose` builds the data-gradient
+// operator: wt[co_f][8-tap][ci_f] (flipped taps, swapped channel roles).
+__global__ void conv_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int KK,
+                                         int out_pad, int transpose) {
+  const int n_in = transpose ? Cout : Cin;    // rows of wt
+  const int n_out = transpose ? Cin : Cout;   // valid columns of wt
+  const size_t total = (size_t)n_in * KK * out_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % out_pad);
+    const int tap = (int)((i / out_pad) % KK);
+    const int rowi = (int)(i / ((size_t)out_pad * KK));
+    float v = 0.f;
+    if (col < n_out) {
+      if (!transpose) v = __ldg(w + ((size_t)col * Cin + rowi) * KK + tap);
+      else v = __ldg(w + ((size_t)rowi * Cin + col) * KK + (KK - 1 - tap));
+    }
+    wt[i] = v;
+  }
+}
+
+// g_conv = grad_out * act'(out)
+__global__ void conv_act_grad_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, float* __restrict__ g,
+                                     size_t n, int act) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float o = __ldg(out + i), go = __ldg(grad_out + i);
+    float d = 1.f;
+    if (act == DD_ACT_ELU) d = o > 0.f ? 1.f : o + 1.f;
+    else if (act == DD_ACT_SIGMOID) d = o * (1.f - o);
+    else if (act == DD_ACT_RELU) d = o > 0.f ? 1.f : 0.f;
+    g[i] = go * d;
+  }
+}
+
+struct RouteArgs {
+  const float* gpad;   // (B, Cin, Hp, Wp) gradient on the (padded) convolution-input grid
+  int B, Cin, H, W;    // virtual input size
+  int Hp, Wp, off;     // padded grid and offset of virtual (0,0) inside it (1 reflect, 0 zero)
+  int reflect;
+  int C0, C1, H0, W0, up0;
+  float* gx0;
+  float* gx1;
+};
+
+__device__ __forceinline__ float folded(const RouteArgs& a, const float* __restrict__ plane, int y, int x) {
+  // sum over the padded positions that ReflectionPad2d(1) maps onto (y, x)
+  float s = 0.f;
+  const int ys[2] = {y, y == 1 ? -1 : (y == a.H - 2 ? a.H : y)};
+  const int xs[2] = {x, x == 1 ? -1 : (x == a.W - 2 ? a.W : x)};
+  const int ny = (a.reflect && ys[1] != y) ? 2 : 1, nx = (a.reflect && xs[1] != x) ? 2 : 1;
+  for (int i = 0; i < ny; ++i)
+    for (int j = 0; j < nx; ++j) s += __ldg(plane + (size_t)(ys[i] + a.off) * a.Wp + xs[j] + a.off);
+  if (a.reflect && a.H == 3 && y == 1) s += 0.f;   // H >= 4 on this path (decoder maps are >= 6x20)
+  return s;
+}
+
+__global__ void conv_route_kernel(const __grid_constant__ RouteArgs a) {
+  const size_t n0 = a.gx0 ? (size_t)a.B * a.C0 * a.H0 * a.W0 : 0;
+  const size_t n1 = a.gx1 ? (size_t)a.B * a.C1 * a.H * a.W : 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n0) {
+      const int x = (int)(i % a.W0), y = (int)((i / a.W0) % a.H0);
+      const int c = (int)((i / ((size_t)a.W0 * a.H0)) % a.C0), b = (int)(i / ((size_t)a.W0 * a.H0 * a.C0));
+      const float* plane = a.gpad + ((size_t)b * a.Cin + c) * a.Hp * a.Wp;
+      float s = 0.f;
+      if (a.up0 == DD_UP_NONE) {
+        s = folded(a, plane, y, x);
+      } else if (a.up0 == DD_UP_NEAREST2) {
+        s = folded(a, plane, 2 * y, 2 * x) + folded(a, plane, 2 * y, 2 * x + 1) + folded(a, plane, 2 * y + 1, 2 * x) +
+            folded(a, plane, 2 * y + 1, 2 * x + 1);
+      } else {
+        for (int yy = 2 * y - 1; yy <= 2 * y + 2; ++yy) {
+          if (yy < 0 || yy >= a.H) continue;
+          const float wy = up_weight(yy, 1, a.H0, y);
+          if (wy == 0.f) continue;
+          for (int xx = 2 * x - 1; xx <= 2 * x + 2; ++xx) {
+            if (xx < 0 || xx >= a.W) continue;
+            const float wx = up_weight(xx, 1, a.W0, x);
+            if (wx != 0.f) s += wy * wx * folded(a, plane, yy, xx);
+          }
+        }
+      }
+      a.gx0[i] = s;
+    } else {
+      const size_t j = i - n0;
+      const int x = (int)(j % a.W), y = (int)((j / a.W) % a.H);
+      const int c = (int)((j / ((size_t)a.W * a.H)) % a.C1), b = (int)(j / ((size_t)a.W * a.H * a.C1));
+      const float* plane = a.gpad + ((size_t)b * a.Cin + a.C0 + c) * a.Hp * a.Wp;
+      a.gx1[j] = folded(a, plane, y, x);
+    }
+  }
+}
+
+// ---- weight gradient -------------------------------------------------------------------------
+constexpr int WG_CO = 32;            // output channels per CTA
+constexpr int WG_GPITCH = CT_H * CT_W + 4;   // 132
+
+struct WgradArgs {
+  VirtIn vin;
+  const float* g;    // (B, Cout, H, W) gradient w.r.t. the convolution output (activation already folded in)
+  int B, H, W, Cin, Cout;
+  int tiles_x, tiles_y;
+  int items_per_split;   // (image, tile) work items per z-slice
+  float* gw;         // (Cout, Cin, k, k), zero-initialised, accumulated with atomics
+};
+
+template <int KS>
+__global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+  constexpr int KK = KS * KS;
+  constexpr int HALO = KS / 2;
+  constexpr int ROWS = CT_H + 2 * HALO, COLS = CT_W + 2 * HALO;
+  __shared__ __align__(16) float g_s[WG_CO * WG_GPITCH];
+  __shared__ __align__(16) float v_s[CI_T * IN_PLANE];
+
+  const int tid = threadIdx.x;
+  const int ci = tid & 7, cp = tid >> 3;   // thread owns output channels co0+2cp, co0+2cp+1 and input channel ci0+ci
+  const int co0 = blockIdx.x * WG_CO, ci0 = blockIdx.y * CI_T;
+  const int n_tiles = a.tiles_x * a.tiles_y;
+  const int n_items = a.B * n_tiles;
+  const int it0 = blockIdx.z * a.items_per_split;
+  const int it1 = min(n_items, it0 + a.items_per_split);
+
+  float acc[2][KK];
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int t = 0; t < KK; ++t) acc[c][t] = 0.f;
+
+  for (int it = it0; it < it1; ++it) {
+    const int b = it / n_tiles, tile = it - b * n_tiles;
+    const int ty0 = (tile / a.tiles_x) * CT_H, tx0 = (tile % a.tiles_x) * CT_W;
+    for (int i = tid; i < WG_CO * CT_H * CT_W; i += CONV_THREADS) {
+      const int c = i / (CT_H * CT_W), px = i - c * (CT_H * CT_W);
+      const int y = ty0 + px / CT_W, x = tx0 + (px % CT_W);
+      float v = 0.f;
+      if (co0 + c < a.Cout && y < a.H && x < a.W) v = __ldg(a.g + (((size_t)b * a.Cout + co0 + c) * a.H + y) * a.W + x);
+      g_s[c * WG_GPITCH + px] = v;
+    }
+    for (int i = tid; i < CI_T * ROWS * COLS; i += CONV_THREADS) {
+      const int c = i / (ROWS * COLS);
+      const int rem = i - c * (ROWS * COLS);
+      const int r = rem / COLS, cc = rem - r * COLS;
+      float v = 0.f;
+      if (ci0 + c < a.Cin) v = virt_load(a.vin, b, ci0 + c, ty0 + r - HALO, tx0 + cc - HALO);
+      v_s[c * IN_PLANE + r * IN_PITCH + cc] = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < CT_H; ++r) {
+#pragma unroll
+      for (int xq = 0; xq < CT_W; xq += 4) {
+        const float4 ga = *reinterpret_cast<const float4*>(g_s + (2 * cp) * WG_GPITCH + r * CT_W + xq);
+        const float4 gb = *reinterpret_cast<const float4*>(g_s + (2 * cp + 1) * WG_GPITCH + r * CT_W + xq);
+        const float g0[4] = {ga.x, ga.y, ga.z, ga.w}, g1[4] = {gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy) {
+          const float* vp = v_s + ci * IN_PLANE + (r + dy) * IN_PITCH + xq;
+          float vr[4 + KS - 1];
+          const float4 v4 = *reinterpret_cast<const float4*>(vp);
+          vr[0] = v4.x, vr[1] = v4.y, vr[2] = v4.z, vr[3] = v4.w;
+          if (KS == 3) {
+            const float2 v2 = *reinterpret_cast<const float2*>(vp + 4);
+            vr[4] = v2.x, vr[5] = v2.y;
+          }
+#pragma unroll
+          for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              acc[0][dy * KS + dx] = fmaf(g0[p], vr[p + dx], acc[0][dy * KS + dx]);
+              acc[1][dy * KS + dx] = fmaf(g1[p], vr[p + dx], acc[1][dy * KS + dx]);
+            }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (ci0 + ci < a.Cin) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int co = co0 + 2 * cp + c;
+      if (co >= a.Cout) continue;
+#pragma unroll
+      for (int t = 0; t < KK; ++t) atomicAdd(a.gw + ((size_t)co * a.Cin + ci0 + ci) * KK + t, acc[c][t]);
+    }
+  }
+}
+
+// grad_bias[co] = sum over b, y, x of g
+__global__ void conv_bias_grad_kernel(const float* __restrict__ g, float* __restrict__ gb, int B, int Cout, int HW) {
+  __shared__ float sh[8];
+  const int co = blockIdx.x;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* p = g + ((size_t)b * Cout + co) * HW;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += __ldg(p + i);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    gb[co] = t;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+static inline int cpt_for(int cout) { return cout >= 48 ? 8 : (cout >= 24 ? 4 : (cout >= 12 ? 2 : 1)); }
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+static int validate_conv(const dd_conv_desc* d) {
+  DD_REQUIRE(d != nullptr, "dd_conv_desc is NULL");
+  DD_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "dd_conv: bad shape");
+  DD_REQUIRE(d->ksize == 1 || d->ksize == 3, "dd_conv: ksize must be 1 or 3");
+  DD_REQUIRE(d->C0 > 0 && d->x0 && d->weight, "dd_conv: x0 / weight missing");
+  DD_REQUIRE(d->C1 >= 0 && (d->C1 == 0 || d->x1), "dd_conv: x1 missing");
+  DD_REQUIRE(d->up0 >= 0 && d->up0 <= 2 && d->act >= 0 && d->act <= 3, "dd_conv: bad up0/act");
+  DD_REQUIRE(d->up0 == DD_UP_NONE || (d->H % 2 == 0 && d->W % 2 == 0), "dd_conv: x2 up-sampling needs even H, W");
+  DD_REQUIRE(!(d->residual && d->act != DD_ACT_NONE), "dd_conv: residual is only supported with DD_ACT_NONE");
+  DD_REQUIRE(!(d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT && (d->H < 4 || d->W < 4)), "dd_conv: reflect pad needs H, W >= 4");
+  return DD_OK;
+}
+
+static VirtIn make_vin(const dd_conv_desc* d) {
+  VirtIn v;
+  v.x0 = d->x0, v.x1 = d->x1, v.C0 = d->C0, v.C1 = d->C1;
+  v.up0 = d->up0;
+  v.H0 = d->up0 == DD_UP_NONE ? d->H : d->H / 2;
+  v.W0 = d->up0 == DD_UP_NONE ? d->W : d->W / 2;
+  v.Hin = d->H, v.Win = d->W;
+  v.pad_mode = d->ksize == 3 ? d->pad_mode : DD_PAD_ZERO;
+  return v;
+}
+
+template <int KS>
+static void launch_core(const ConvArgs& args, int cpt, dim3 grid_base, cudaStream_t st) {
+  dim3 grid = grid_base;
+  grid.y = (args.Cout + 8 * cpt - 1) / (8 * cpt);
+  if (cpt == 8) conv_core_kernel<KS, 8><<<grid, CONV_THREADS, 0, st>>>(args);
+  else if (cpt == 4) conv_core_kernel<KS, 4><<<grid, CONV_THREADS, 0, st>>>(args);
+  else if (cpt == 2) conv_core_kernel<KS, 2><<<grid, CONV_THREADS, 0, st>>>(args);
+  else conv_core_kernel<KS, 1><<<grid, CONV_THREADS, 0, st>>>(args);
+}
+
+static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose,
+                    cudaStream_t st) {
+  const int KK = ks * ks;
+  const int cpt = cpt_for(args.Cout);
+  args.cout_pad = round_up(args.Cout, 8 * cpt);
+  const size_t wn = (size_t)args.Cin * KK * args.cout_pad;
+  conv_prep_weights_kernel<<<(int)((wn + 255) / 256 < 592 ? (wn + 255) / 256 : 592), 256, 0, st>>>(
+      w_oihw, wt_buf, Cout_f, Cin_f, KK, args.cout_pad, transpose ? 1 : 0);
+  args.wt = wt_buf;
+  args.tiles_x = (args.Wo + CT_W - 1) / CT_W;
+  const int tiles_y = (args.Ho + CT_H - 1) / CT_H;
+  dim3 grid(args.tiles_x * tiles_y, 1, args.B);
+  if (ks == 3) launch_core<3>(args, cpt, grid, st);
+  else launch_core<1>(args, cpt, grid, st);
+  DD_CHECK_CUDA(cudaGetLastError());
+  return DD_OK;
+}
+
+struct ConvWs {
+  size_t wt, gconv, wtd, gpad, total;
+};
+
+static ConvWs conv_ws(const dd_conv_desc* d) {
+  ConvWs w;
+  const int KK = d->ksize * d->ksize;
+  const int Cin = d->C0 + d->C1;
+  const size_t wt_f = (size_t)Cin * KK * round_up(d->Cout, 8 * cpt_for(d->Cout)) * sizeof(float);
+  const size_t wt_d = (size_t)d->Cout * KK * round_up(Cin, 8 * cpt_for(Cin)) * sizeof(float);
+  const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
+  const size_t Hp = d->H + (reflect ? 2 : 0), Wp = d->W + (reflect ? 2 : 0);
+  w.wt = 0;
+  w.gconv = align256(wt_f);
+  w.wtd = w.gconv + align256((size_t)d->B * d->Cout * d->H * d->W * sizeof(float));
+  w.gpad = w.wtd + align256(wt_d);
+  w.total = w.gpad + align256((size_t)d->B * Cin * Hp * Wp * sizeof(float));
+  return w;
+}
+
+int conv_fwd_impl(const dd_conv_desc* d, float* out, void* workspace, size_t bytes, cudaStream_t st) {
+  int rc = validate_conv(d);
+  if (rc != DD_OK) return rc;
+  DD_REQUIRE(out != nullptr, "dd_conv_fwd: out is NULL");
+  const ConvWs ws = conv_ws(d);
+  if (!workspace || bytes < ws.gconv) {
+    set_error("dd_conv_fwd: workspace too small (%zu < %zu)", bytes, ws.gconv);
+    return DD_ERR_WORKSPACE;
+  }
+  ConvArgs args;
+  memset(&args, 0, sizeof(args));
+  args.vin = make_vin(d);
+  args.B = d->B, args.Ho = d->H, args.Wo = d->W, args.oy = 0, args.ox = 0;
+  args.Cin = d->C0 + d->C1, args.Cout = d->Cout;
+  args.bias = d->bias, args.residual = d->residual, args.act = d->act, args.out = out;
+  return run_core(args, d->ksize, reinterpret_cast<float*>((char*)workspace + ws.wt), d->weight, d->Cout, args.Cin, false, st);
+}
+
+int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out, float* grad_x0, float* grad_x1,
+                  float* grad_weight, float* grad_bias, void* workspace, size_t bytes, cudaStream_t st) {
+  int rc = validate_conv(d);
+  if (rc != DD_OK) return rc;
+  DD_REQUIRE(grad_out != nullptr, "dd_conv_bwd: grad_out is NULL");
+  DD_REQUIRE(d->act == DD_ACT_NONE || out != nullptr, "dd_conv_bwd: forward output required for the activation derivative");
+  const ConvWs ws = conv_ws(d);
+  if (!workspace || bytes < ws.total) {
+    set_error("dd_conv_bwd: workspace too small (%zu < %zu)", bytes, ws.total);
+    return DD_ERR_WORKSPACE;
+  }
+  const int Cin = d->C0 + d->C1, KK = d->ksize * d->ksize;
+  const size_t n_out = (size_t)d->B * d->Cout * d->H * d->W;
+  const float* g = grad_out;
+  if (d->act != DD_ACT_NONE) {
+    float* gc = reinterpret_cast<float*>((char*)workspace + ws.gconv);
+    conv_act_grad_kernel<<<(int)((n_out + 255) / 256 < 2368 ? (n_out + 255) / 256 : 2368), 256, 0, st>>>(grad_out, out, gc, n_out, d->act);
+    g = gc;
+  }
+  if (grad_bias) conv_bias_grad_kernel<<<d->Cout, 256, 0, st>>>(g, grad_bias, d->B, d->Cout, d->H * d->W);
+  if (grad_weight) {
+    DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));
+    WgradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.vin = make_vin(d);
+    wa.g = g, wa.B = d->B, wa.H = d->H, wa.W = d->W, wa.Cin = Cin, wa.Cout = d->Cout, wa.gw = grad_weight;
+    wa.tiles_x = (d->W + CT_W - 1) / CT_W, wa.tiles_y = (d->H + CT_H - 1) / CT_H;
+    const int n_items = d->B * wa.tiles_x * wa.tiles_y;
+    const int gx = (d->Cout + WG_CO - 1) / WG_CO, gy = (Cin + CI_T - 1) / CI_T;
+    int splits = (148 * 8 + gx * gy - 1) / (gx * gy);   // ~8 CTAs per SM in flight
+    splits = splits < 1 ? 1 : (splits > n_items ? n_items : splits);
+    wa.items_per_split = (n_items + splits - 1) / splits;
+    splits = (n_items + wa.items_per_split - 1) / wa.items_per_split;
+    dim3 grid(gx, gy, splits);
+    if (d->ksize == 3) conv_wgrad_kernel<3><<<grid, CONV_THREADS, 0, st>>>(wa);
+    else conv_wgrad_kernel<1><<<grid, CONV_THREADS, 0, st>>>(wa);
+  }
+  if (grad_x0 || grad_x1) {
+    const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
+    float* gpad = reinterpret_cast<float*>((char*)workspace + ws.gpad);
+    ConvArgs args;
+    memset(&args, 0, sizeof(args));
+    args.vin.x0 = g, args.vin.x1 = nullptr, args.vin.C0 = d->Cout, args.vin.C1 = 0;
+    args.vin.H0 = d->H, args.vin.W0 = d->W, args.vin.up0 = DD_UP_NONE, args.vin.Hin = d->H, args.vin.Win = d->W;
+    args.vin.pad_mode = DD_PAD_ZERO;
+    args.B = d->B;
+    args.Ho = d->H + (reflect ? 2 : 0), args.Wo = d->W + (reflect ? 2 : 0);
+    args.oy = reflect ? -1 : 0, args.ox = reflect ? -1 : 0;
+    args.Cin = d->Cout, args.Cout = Cin;
+    args.act = DD_ACT_NONE, args.out = gpad;
+    rc = run_core(args, d->ksize, reinterpret_cast<float*>((char*)workspace + ws.wtd), d->weight, d->Cout, Cin, true, st);
+    if (rc != DD_OK) return rc;
+    RouteArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.gpad = gpad, ra.B = d->B, ra.Cin = Cin, ra.H = d->H, ra.W = d->W;
+    ra.Hp = args.Ho, ra.Wp = args.Wo, ra.off = reflect ? 1 : 0, ra.reflect = reflect ? 1 : 0;
+    ra.C0 = d->C0, ra.C1 = d->C1, ra.up0 = d->up0;
+    ra.H0 = d->up0 == DD_UP_NONE ? d->H : d->H / 2, ra.W0 = d->up0 == DD_UP_NONE ? d->W : d->W / 2;
+    ra.gx0 = grad_x0, ra.gx1 = d->C1 > 0 ? grad_x1 : nullptr;
+    const size_t n = (grad_x0 ? (size_t)d->B * d->C0 * ra.H0 * ra.W0 : 0) + (ra.gx1 ? (size_t)d->B * d->C1 * d->H * d->W : 0);
+    if (n > 0) conv_route_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(ra);
+  }
+  DD_CHECK_CUDA(cudaGetLastError());
+  return DD_OK;
+}
+
+// ---- bilinear resize (align_corners=False), general sizes -----------------------------------------
+__device__ __forceinline__ void resize_taps(int dst, int n_in, int n_out, int& i0, int& i1, float& l) {
+  if (n_in == n_out) {
+    i0 = i1 = dst, l = 0.f;
+    return;
+  }
+  const float scale = (float)n_in / (float)n_out;
+  const float src = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
+  i0 = min((int)src, n_in - 1);
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l = src - (float)i0;
+}
+
+__global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int BC, int hi, int wi, int ho, int wo,
+                                  int sigmoid) {
+  const size_t n = (size_t)BC * ho * wo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % wo), yo = (int)((i / wo) % ho);
+    const size_t bc = i / ((size_t)wo * ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_taps(yo, hi, ho, y0, y1, ly);
+    resize_taps(xo, wi, wo, x0, x1, lx);
+    const float* p = x + bc * hi * wi;
+    float v = (1.f - ly) * ((1.f - lx) * __ldg(p + y0 * wi + x0) + lx * __ldg(p + y0 * wi + x1)) +
+              ly * ((1.f - lx) * __ldg(p + y1 * wi + x0) + lx * __ldg(p + y1 * wi + x1));
+    if (sigmoid) v = 1.f / (1.f + expf(-v));
+    out[i] = v;
+  }
+}
+
+__global__ void resize_bwd_kernel(const float* __restrict__ go, const float* __restrict__ out, float* __restrict__ gx, int BC,
+                                  int hi, int wi, int ho, int wo, int sigmoid) {
+  const size_t n = (size_t)BC * ho * wo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(i % wo), yo = (int)((i / wo) % ho);
+    const size_t bc = i / ((size_t)wo * ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    resize_taps(yo, hi, ho, y0, y1, ly);
+    resize_taps(xo, wi, wo, x0, x1, lx);
+    float g = __ldg(go + i);
+    if (sigmoid) {
+      const float o = __ldg(out + i);
+      g *= o * (1.f - o);
+    }
+    float* p = gx + bc * hi * wi;
+    atomicAdd(p + y0 * wi + x0, g * (1.f - ly) * (1.f - lx));
+    atomicAdd(p + y0 * wi + x1, g * (1.f - ly) * lx);
+    atomicAdd(p + y1 * wi + x0, g * ly * (1.f - lx));
+    atomicAdd(p + y1 * wi + x1, g * ly * lx);
+  }
+}
+
+}  // namespace dd
+
+extern "C" {
+
+size_t dd_conv_workspace_bytes(const dd_conv_desc* d) {
+  if (!d || d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cout <= 0 || d->C0 <= 0 || (d->ksize != 1 && d->ksize != 3)) return 0;
+  return dd::conv_ws(d).total;
+}
+
+int dd_conv_fwd(const dd_conv_desc* desc, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return dd::conv_fwd_impl(desc, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dd_conv_bwd(const dd_conv_desc* desc, const float* out, const float* grad_out, float* grad_x0, float* grad_x1,
+                float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes, void* stream) {
+  return dd::conv_bwd_impl(desc, out, grad_out, grad_x0, grad_x1, grad_weight, grad_bias, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+
+int dd_resize_bilinear_fwd(const float* x, int BC, int h_in, int w_in, int h_out, int w_out, int sigmoid, float* out,
+                           void* stream) {
+  using namespace dd;
+  DD_REQUIRE(x && out && BC > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0, "dd_resize_bilinear_fwd: bad arguments");
+  const size_t n = (size_t)BC * h_out * w_out;
+  resize_fwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, (cudaStream_t)stream>>>(
+      x, out, BC, h_in, w_in, h_out, w_out, sigmoid);
+  DD_CHECK_CUDA(cudaGetLastError());
+  return DD_OK;
+}
+
+int dd_resize_bilinear_bwd(const float* grad_out, const float* out, int BC, int h_in, int w_in, int h_out, int w_out,
+                           int sigmoid, float* grad_x, void* stream) {
+  using namespace dd;
+  DD_REQUIRE(grad_out && grad_x && BC > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0, "dd_resize_bilinear_bwd: bad arguments");
+  DD_REQUIRE(!sigmoid || out, "dd_resize_bilinear_bwd: forward output required with sigmoid");
+  cudaStream_t st = (cudaStream_t)stream;
+  DD_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)BC * h_in * w_in * sizeof(float), st));
+  const size_t n = (size_t)BC * h_out * w_out;
+  resize_bwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(grad_out, out, grad_x, BC, h_in,
+                                                                                            w_in, h_out, w_out, sigmoid);
+  DD_CHECK_CUDA(cudaGetLastError());
+  return DD_OK;
+}
+
+}  // extern "C"

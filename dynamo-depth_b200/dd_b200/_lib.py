@@ -63,6 +63,30 @@ class WarpGrads(C.Structure):
     ]
 
 
+DD_MAX_SMOOTH_TASKS = 24
+
+
+class SmoothTask(C.Structure):
+    _fields_ = [
+        ("inp", FP), ("img", FP), ("grad_inp", FP),
+        ("B", C.c_int32), ("C", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("mean_normalise", C.c_int32),
+    ]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32),
+        ("ksize", C.c_int32), ("pad_mode", C.c_int32), ("act", C.c_int32), ("up0", C.c_int32),
+        ("C0", C.c_int32), ("C1", C.c_int32),
+        ("x0", FP), ("x1", FP), ("weight", FP), ("bias", FP), ("residual", FP),
+    ]
+
+
+PAD_ZERO, PAD_REFLECT = 0, 1
+UP_NONE, UP_NEAREST2, UP_BILINEAR2 = 0, 1, 2
+ACT_NONE, ACT_ELU, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3
+
 # symbol -> (restype, argtypes); tests check that the .so exports exactly the header's entry points
 SIGNATURES = {
     "dd_last_error": (C.c_char_p, []),
@@ -71,6 +95,17 @@ SIGNATURES = {
     "dd_warp_photo_workspace_bytes": (C.c_size_t, [C.POINTER(WarpDesc)]),
     "dd_warp_photo_fwd": (C.c_int, [C.POINTER(WarpDesc), C.POINTER(WarpAux), FP, FP, C.c_size_t, FP]),
     "dd_warp_photo_bwd": (C.c_int, [C.POINTER(WarpDesc), FP, C.POINTER(WarpAux), C.POINTER(WarpGrads), FP, C.c_size_t, FP]),
+    "dd_smooth_workspace_bytes": (C.c_size_t, [C.POINTER(SmoothTask), C.c_int]),
+    "dd_smooth_fwd": (C.c_int, [C.POINTER(SmoothTask), C.c_int, FP, FP, C.c_size_t, FP]),
+    "dd_smooth_bwd": (C.c_int, [C.POINTER(SmoothTask), C.c_int, FP, FP, C.c_size_t, FP]),
+    "dd_msparsity_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dd_msparsity_fwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, C.c_size_t, FP]),
+    "dd_msparsity_bwd": (C.c_int, [FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_conv_workspace_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "dd_conv_fwd": (C.c_int, [C.POINTER(ConvDesc), FP, FP, C.c_size_t, FP]),
+    "dd_conv_bwd": (C.c_int, [C.POINTER(ConvDesc), FP, FP, FP, FP, FP, FP, FP, C.c_size_t, FP]),
+    "dd_resize_bilinear_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_resize_bilinear_bwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
 }
 
 _lib = None

@@ -233,3 +233,227 @@ def view_synthesis_sums(cfg: WarpConfig, target, sources, K, inv_K, Ts, tss, dis
         if cfg.motmask:
             args += [_prep(x) for x in masks[i]]
     return _ViewSynthesisFn.apply(cfg, nF, *args)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge-aware smoothness (tools.compute_smooth_loss, tools.py:311-326), batched
+# ---------------------------------------------------------------------------------------------
+
+
+def _smooth_tasks(inps, imgs, norms, grads=None):
+    n = len(inps)
+    arr = (L.SmoothTask * n)()
+    for i in range(n):
+        B, Cc, h, w = inps[i].shape
+        arr[i].inp = L.ptr(inps[i])
+        arr[i].img = L.ptr(imgs[i]) if imgs[i] is not None else None
+        arr[i].grad_inp = grads[i].data_ptr() if grads is not None and grads[i] is not None else None
+        arr[i].B, arr[i].C, arr[i].h, arr[i].w = B, Cc, h, w
+        arr[i].mean_normalise = 1 if norms[i] else 0
+        if imgs[i] is not None:
+            assert imgs[i].shape == (B, 3, h, w), (imgs[i].shape, inps[i].shape)
+    return arr
+
+
+class _SmoothFn(torch.autograd.Function):
+    """inputs: norms (tuple of bool), n, inp_0..inp_{n-1}, img_0..img_{n-1}; returns (n, 2) sums."""
+
+    @staticmethod
+    def forward(ctx, norms, n, *tensors):
+        lib = L.load()
+        inps, imgs = tensors[:n], tensors[n:]
+        tasks = _smooth_tasks(inps, imgs, norms)
+        dev = inps[0].device
+        sums = torch.empty(n, 2, device=dev)
+        nbytes = lib.dd_smooth_workspace_bytes(tasks, n)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        L.check(lib.dd_smooth_fwd(tasks, n, sums.data_ptr(), ws.data_ptr(), nbytes, _stream()), "dd_smooth_fwd")
+        ctx.norms, ctx.n = norms, n
+        ctx.save_for_backward(*tensors)
+        return sums
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        lib = L.load()
+        n, norms = ctx.n, ctx.norms
+        tensors = ctx.saved_tensors
+        inps, imgs = tensors[:n], tensors[n:]
+        need = ctx.needs_input_grad[2:2 + n]
+        grads = [torch.empty_like(inps[i]) if need[i] else None for i in range(n)]
+        tasks = _smooth_tasks(inps, imgs, norms, grads)
+        dev = inps[0].device
+        nbytes = lib.dd_smooth_workspace_bytes(tasks, n)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        gs = grad_sums.contiguous().float()
+        L.check(lib.dd_smooth_bwd(tasks, n, gs.data_ptr(), ws.data_ptr(), nbytes, _stream()), "dd_smooth_bwd")
+        return (None, None) + tuple(grads) + (None,) * n
+
+
+def smooth_sums(inps, imgs, norms):
+    """inps[i] (B,C,h,w), imgs[i] (B,3,h,w) or None, norms[i] bool -> (n,2) tensor of (sum_x, sum_y)."""
+    n = len(inps)
+    if n == 0:
+        raise ValueError("smooth_sums: no tasks")
+    if not inps[0].is_cuda:
+        raise L.DynamoB200Error("smooth_sums needs CUDA tensors (no CPU fallback)")
+    return _SmoothFn.apply(tuple(bool(x) for x in norms), n, *[_prep(x) for x in inps], *[_prep(x) for x in imgs])
+
+
+def smooth_means(sums, shapes):
+    """(n,2) sums -> per-task  mean_x + mean_y  (tools.py:326) as an (n,) tensor."""
+    den = torch.tensor([[B * Cc * h * (w - 1), B * Cc * (h - 1) * w] for (B, Cc, h, w) in shapes], dtype=torch.float32,
+                       device=sums.device)
+    return (sums / den).sum(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# motion-mask sparsity (Trainer.py:388-399)
+# ---------------------------------------------------------------------------------------------
+
+
+class _MSparsityFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mag, mag_sum, prob):
+        lib = L.load()
+        B, _, h, w = prob.shape
+        dev = prob.device
+        out = torch.empty(4, device=dev)
+        nbytes = lib.dd_msparsity_workspace_bytes(B, h, w)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        L.check(lib.dd_msparsity_fwd(L.ptr(mag), mag_sum.data_ptr(), L.ptr(prob), B, h, w, out.data_ptr(), ws.data_ptr(),
+                                     nbytes, _stream()), "dd_msparsity_fwd")
+        ctx.save_for_backward(mag, mag_sum, prob, out)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = L.load()
+        mag, mag_sum, prob, out = ctx.saved_tensors
+        B, _, h, w = prob.shape
+        grad_prob = torch.empty_like(prob)
+        go = grad_out.contiguous().float().reshape(1)
+        L.check(lib.dd_msparsity_bwd(L.ptr(mag), mag_sum.data_ptr(), L.ptr(prob), out.data_ptr(), go.data_ptr(), B, h, w,
+                                     grad_prob.data_ptr(), _stream()), "dd_msparsity_bwd")
+        return None, None, grad_prob
+
+
+def motion_sparsity(mag, mag_sum, prob):
+    """mag (B,h,w) and its batch sum (0-dim/1-elem device tensor) from the fused forward; prob (B,1,h,w)."""
+    if not prob.is_cuda:
+        raise L.DynamoB200Error("motion_sparsity needs CUDA tensors (no CPU fallback)")
+    return _MSparsityFn.apply(_prep(mag), mag_sum.contiguous(), _prep(prob))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused decoder convolution (layers.py:85-121 ConvBlock / Conv3x3 / upsample + skip concat)
+# ---------------------------------------------------------------------------------------------
+
+_WS_CACHE = {}
+
+
+def _workspace(nbytes, dev):
+    """Per-device scratch buffer reused across calls (stream-ordered, so reuse on one stream is safe)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = buf
+    return buf
+
+
+def _conv_desc(x0, x1, weight, bias, residual, ksize, pad_mode, act, up0):
+    d = L.ConvDesc()
+    B, C0, H0, W0 = x0.shape
+    H, W = (H0, W0) if up0 == L.UP_NONE else (2 * H0, 2 * W0)
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    C1 = x1.shape[1] if x1 is not None else 0
+    if Cin != C0 + C1 or weight.shape[2] != ksize or weight.shape[3] != ksize:
+        raise ValueError(f"conv weight {tuple(weight.shape)} does not match inputs C0={C0} C1={C1} k={ksize}")
+    if x1 is not None and tuple(x1.shape) != (B, C1, H, W):
+        raise ValueError(f"skip tensor {tuple(x1.shape)} != {(B, C1, H, W)}")
+    d.B, d.H, d.W, d.Cout = B, H, W, Cout
+    d.ksize, d.pad_mode, d.act, d.up0 = ksize, pad_mode, act, up0
+    d.C0, d.C1 = C0, C1
+    d.x0, d.x1 = L.ptr(x0), L.ptr(x1)
+    d.weight, d.bias, d.residual = L.ptr(weight), L.ptr(bias), L.ptr(residual)
+    return d, (B, Cout, H, W)
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, residual, ksize, pad_mode, act, up0):
+        lib = L.load()
+        d, oshape = _conv_desc(x0, x1, weight, bias, residual, ksize, pad_mode, act, up0)
+        out = torch.empty(oshape, device=x0.device)
+        nbytes = lib.dd_conv_workspace_bytes(C.byref(d))
+        ws = _workspace(nbytes, x0.device)
+        L.check(lib.dd_conv_fwd(C.byref(d), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "dd_conv_fwd")
+        ctx.cfg = (ksize, pad_mode, act, up0)
+        ctx.has = (x1 is not None, bias is not None, residual is not None)
+        ctx.save_for_backward(x0, x1, weight, bias, out if act != L.ACT_NONE else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = L.load()
+        x0, x1, weight, bias, out = ctx.saved_tensors
+        ksize, pad_mode, act, up0 = ctx.cfg
+        grad_out = grad_out.contiguous()
+        d, _ = _conv_desc(x0, x1, weight, bias, None, ksize, pad_mode, act, up0)
+        need = ctx.needs_input_grad
+        gx0 = torch.empty_like(x0) if need[0] else None
+        gx1 = torch.empty_like(x1) if (x1 is not None and need[1]) else None
+        gw = torch.empty_like(weight) if need[2] else None
+        gb = torch.empty_like(bias) if (bias is not None and need[3]) else None
+        nbytes = lib.dd_conv_workspace_bytes(C.byref(d))
+        ws = _workspace(nbytes, x0.device)
+        p = lambda t: t.data_ptr() if t is not None else None
+        L.check(lib.dd_conv_bwd(C.byref(d), p(out), grad_out.data_ptr(), p(gx0), p(gx1), p(gw), p(gb), ws.data_ptr(),
+                                ws.numel(), _stream()), "dd_conv_bwd")
+        gres = grad_out if (ctx.has[2] and need[4]) else None
+        return gx0, gx1, gw, gb, gres, None, None, None, None
+
+
+def conv2d_fused(x0, weight, bias=None, *, x1=None, residual=None, ksize=3, pad="reflect", act="none", up="none"):
+    """out = act(conv_k(pad(cat(up(x0), x1))) + bias) [+ residual]   (hand-written sm_100a kernels, no fallback)."""
+    if not x0.is_cuda:
+        raise L.DynamoB200Error("conv2d_fused needs CUDA tensors (no CPU fallback)")
+    pad_mode = {"zero": L.PAD_ZERO, "reflect": L.PAD_REFLECT}[pad]
+    act_id = {"none": L.ACT_NONE, "elu": L.ACT_ELU, "sigmoid": L.ACT_SIGMOID, "relu": L.ACT_RELU}[act]
+    up_id = {"none": L.UP_NONE, "nearest": L.UP_NEAREST2, "bilinear": L.UP_BILINEAR2}[up]
+    return _ConvFn.apply(_prep(x0), _prep(x1), _prep(weight), _prep(bias), _prep(residual), ksize, pad_mode, act_id, up_id)
+
+
+class _ResizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size, sigmoid):
+        lib = L.load()
+        lead = x.shape[:-2]
+        hi, wi = x.shape[-2:]
+        ho, wo = size
+        BC = int(x.numel() // (hi * wi))
+        out = torch.empty(*lead, ho, wo, device=x.device)
+        L.check(lib.dd_resize_bilinear_fwd(x.data_ptr(), BC, hi, wi, ho, wo, int(sigmoid), out.data_ptr(), _stream()),
+                "dd_resize_bilinear_fwd")
+        ctx.dims = (BC, hi, wi, ho, wo, int(sigmoid))
+        ctx.save_for_backward(out if sigmoid else None)
+        ctx.in_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = L.load()
+        (out,) = ctx.saved_tensors
+        BC, hi, wi, ho, wo, sig = ctx.dims
+        grad_out = grad_out.contiguous()
+        gx = torch.empty(ctx.in_shape, device=grad_out.device)
+        L.check(lib.dd_resize_bilinear_bwd(grad_out.data_ptr(), out.data_ptr() if out is not None else None, BC, hi, wi, ho,
+                                           wo, sig, gx.data_ptr(), _stream()), "dd_resize_bilinear_bwd")
+        return gx, None, None
+
+
+def resize_bilinear(x, size, sigmoid=False):
+    """F.interpolate(x, size, mode='bilinear', align_corners=False) [+ sigmoid]  (utils.py:98-101)."""
+    if not x.is_cuda:
+        raise L.DynamoB200Error("resize_bilinear needs CUDA tensors (no CPU fallback)")
+    return _ResizeFn.apply(_prep(x), (int(size[0]), int(size[1])), bool(sigmoid))

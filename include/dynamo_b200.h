@@ -114,6 +114,98 @@ typedef struct dd_warp_grads {
 int dd_warp_photo_bwd(const dd_warp_desc* desc, const float* grad_sums, const dd_warp_aux* saved,
                       const dd_warp_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Edge-aware smoothness, batched over every (term, level) of a step
+ *   replaces tools.compute_smooth_loss (tools.py:311-326) and the mean-normalised disparity of
+ *   Trainer.py:357-358:  sum_x = sum |n[..,:-1]-n[..,1:]| * exp(-mean_c|img[..,:-1]-img[..,1:]|),
+ *   sum_y likewise along rows, n = inp / (mean_hw(inp) + 1e-7) when mean_normalise is set.
+ *   The caller divides by the element counts B*C*h*(w-1) and B*C*(h-1)*w (two separate means).
+ * ------------------------------------------------------------------------------------------ */
+#define DD_MAX_SMOOTH_TASKS 24
+typedef struct dd_smooth_task {
+  const float* inp;       /* (B,C,h,w) */
+  const float* img;       /* (B,3,h,w) colour of the same level, or NULL (no edge weights) */
+  float* grad_inp;        /* backward output (B,C,h,w), overwritten; NULL = skip this task */
+  int32_t B, C, h, w;
+  int32_t mean_normalise; /* Trainer.py:357-358 */
+} dd_smooth_task;
+
+size_t dd_smooth_workspace_bytes(const dd_smooth_task* tasks, int ntasks);
+/* sums: device (ntasks, 2) = (sum_x, sum_y) */
+int dd_smooth_fwd(const dd_smooth_task* tasks, int ntasks, float* sums, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* grad_sums: device (ntasks, 2) upstream gradients of (sum_x, sum_y) */
+int dd_smooth_bwd(const dd_smooth_task* tasks, int ntasks, const float* grad_sums, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Motion-mask sparsity (Trainer.py:388-399)
+ *   static = mag < mean(mag)   (mag = ||down(sample_ego)-down(sample_complete)||^2 from
+ *   dd_warp_photo_fwd, mean over the whole batch), loss = mean over static pixels of
+ *   BCEWithLogits(prob, 0) = softplus(prob), skipped (0) unless every image has a static pixel.
+ *   The reference's two host synchronisations (torch.all / boolean indexing) become a
+ *   device-side guard.
+ *   out[0] = loss, out[1] = guard / count (backward scale), out[2] = guard, out[3] = count
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_msparsity_workspace_bytes(int B, int h, int w);
+int dd_msparsity_fwd(const float* mag, const float* mag_sum, const float* prob, int B, int h, int w, float* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* grad_prob (B,1,h,w) = grad_out[0] * out[1] * static * sigmoid(prob), overwritten */
+int dd_msparsity_bwd(const float* mag, const float* mag_sum, const float* prob, const float* out,
+                     const float* grad_out, int B, int h, int w, float* grad_prob, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused decoder convolution (fp32 SIMT implicit GEMM; tensor cores are reserved for the encoders)
+ *   replaces networks/layers.py ConvBlock / Conv3x3 / upsample (layers.py:85-121) as used by
+ *   DepthDecoder / LiteDepthDecoder (depth_decoder.py:40-55,99-115), the refine convolutions of
+ *   MotionDecoder (motion_decoder.py:24-62) and the PoseDecoder convolutions (pose_decoder.py:16-37):
+ *     out = act( conv_k( pad( concat( up(x0), x1 ) ) ) + bias ) [+ residual]
+ *   with pad = ReflectionPad2d(1) | zero, up = none | nearest x2 | bilinear x2 (align_corners=False),
+ *   act = none | ELU | sigmoid | ReLU, all in one pass over the inputs.
+ * ------------------------------------------------------------------------------------------ */
+#define DD_PAD_ZERO 0
+#define DD_PAD_REFLECT 1
+#define DD_UP_NONE 0
+#define DD_UP_NEAREST2 1
+#define DD_UP_BILINEAR2 2
+#define DD_ACT_NONE 0
+#define DD_ACT_ELU 1
+#define DD_ACT_SIGMOID 2
+#define DD_ACT_RELU 3
+
+typedef struct dd_conv_desc {
+  int32_t B, H, W;       /* output (= convolution input) spatial size */
+  int32_t Cout;
+  int32_t ksize;         /* 1 or 3 (stride 1, "same" padding) */
+  int32_t pad_mode;      /* DD_PAD_* (ignored for ksize 1) */
+  int32_t act;           /* DD_ACT_* */
+  int32_t up0;           /* DD_UP_*: how x0 reaches (H, W) */
+  int32_t C0, C1;        /* channels of x0 and of the optional skip tensor x1 (0 = none) */
+  const float* x0;       /* (B,C0,H,W) or (B,C0,H/2,W/2) when up0 != DD_UP_NONE */
+  const float* x1;       /* (B,C1,H,W) or NULL */
+  const float* weight;   /* (Cout, C0+C1, k, k) OIHW as in nn.Conv2d */
+  const float* bias;     /* (Cout) or NULL */
+  const float* residual; /* (B,Cout,H,W) added after the activation, or NULL */
+} dd_conv_desc;
+
+size_t dd_conv_workspace_bytes(const dd_conv_desc* desc);
+int dd_conv_fwd(const dd_conv_desc* desc, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* out: forward result (needed for ELU / sigmoid / ReLU derivatives, may be NULL for DD_ACT_NONE);
+ * grad_x0 / grad_x1 / grad_weight / grad_bias may each be NULL (skipped); all are overwritten.
+ * The gradient w.r.t. `residual` is grad_out itself. */
+int dd_conv_bwd(const dd_conv_desc* desc, const float* out, const float* grad_out, float* grad_x0, float* grad_x1,
+                float* grad_weight, float* grad_bias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bilinear resize, align_corners=False (utils.interp, utils.py:98-101; F.interpolate at
+ * motion_decoder.py:38 and depth_decoder.py:112), optional fused sigmoid (depth_decoder.py:113).
+ * ------------------------------------------------------------------------------------------ */
+int dd_resize_bilinear_fwd(const float* x, int BC, int h_in, int w_in, int h_out, int w_out, int sigmoid, float* out,
+                           void* stream);
+/* grad_x (BC,h_in,w_in) overwritten; `out` is the forward result (needed when sigmoid != 0) */
+int dd_resize_bilinear_bwd(const float* grad_out, const float* out, int BC, int h_in, int w_in, int h_out, int w_out,
+                           int sigmoid, float* grad_x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,94 @@
+"""GPU parity of the fused decoder convolution / resize kernels against plain PyTorch fp32 (TF32 off)
+restating the reference layer semantics (layers.py:85-121, motion_decoder.py:24-62)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def ref_conv(x0, w, b, x1, residual, ksize, pad, act, up):
+    if up == "nearest":
+        x0 = F.interpolate(x0, scale_factor=2, mode="nearest")
+    elif up == "bilinear":
+        x0 = F.interpolate(x0, scale_factor=2, mode="bilinear")
+    x = torch.cat([x0, x1], 1) if x1 is not None else x0
+    if ksize == 3:
+        x = F.pad(x, (1, 1, 1, 1), mode="reflect" if pad == "reflect" else "constant")
+    y = F.conv2d(x, w, b)
+    y = {"none": lambda t: t, "elu": F.elu, "sigmoid": torch.sigmoid, "relu": F.relu}[act](y)
+    return y + residual if residual is not None else y
+
+
+CASES = [
+    # B, C0, C1, Cout, H, W (output), ksize, pad, act, up, residual
+    (2, 16, 0, 16, 16, 32, 3, "reflect", "elu", "none", False),
+    (2, 24, 8, 20, 12, 40, 3, "reflect", "elu", "nearest", False),
+    (2, 14, 16, 14, 12, 40, 3, "reflect", "elu", "bilinear", False),
+    (3, 112, 0, 1, 24, 80, 3, "reflect", "none", "none", False),
+    (2, 32, 0, 1, 6, 20, 3, "reflect", "sigmoid", "none", False),
+    (2, 3, 64, 64, 6, 20, 3, "zero", "none", "none", False),
+    (2, 1, 9, 9, 20, 36, 3, "zero", "none", "none", False),
+    (2, 64, 64, 3, 12, 40, 1, "zero", "none", "none", True),
+    (2, 70, 0, 48, 6, 20, 1, "zero", "relu", "none", False),
+    (2, 40, 0, 40, 6, 20, 3, "zero", "relu", "none", False),
+    (1, 128, 64, 112, 24, 80, 3, "reflect", "elu", "bilinear", False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
+def test_conv_fwd_bwd(case):
+    from dd_b200.functional import conv2d_fused
+
+    B, C0, C1, Cout, H, W, ks, pad, act, up, use_res = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 10000)
+    h0, w0 = (H, W) if up == "none" else (H // 2, W // 2)
+    x0 = torch.randn(B, C0, h0, w0, device="cuda", generator=g, requires_grad=True)
+    x1 = torch.randn(B, C1, H, W, device="cuda", generator=g, requires_grad=True) if C1 else None
+    w = (torch.randn(Cout, C0 + C1, ks, ks, device="cuda", generator=g) / ((C0 + C1) * ks * ks) ** 0.5).requires_grad_(True)
+    b = (0.1 * torch.randn(Cout, device="cuda", generator=g)).requires_grad_(True)
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g, requires_grad=True) if use_res else None
+    go = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+
+    out = conv2d_fused(x0, w, b, x1=x1, residual=res, ksize=ks, pad=pad, act=act, up=up)
+    out.backward(go)
+    got = [out.detach()] + [t.grad.clone() for t in (x0, x1, w, b, res) if t is not None]
+    for t in (x0, x1, w, b, res):
+        if t is not None:
+            t.grad = None
+    ref = ref_conv(x0, w, b, x1, res, ks, pad, act, up)
+    ref.backward(go)
+    exp = [ref.detach()] + [t.grad.clone() for t in (x0, x1, w, b, res) if t is not None]
+    names = ["out"] + [n for n, t in zip(["gx0", "gx1", "gw", "gb", "gres"], (x0, x1, w, b, res)) if t is not None]
+    for n, a, e in zip(names, got, exp):
+        scale = e.abs().max().item() + 1e-12
+        err = (a - e).abs().max().item()
+        assert err <= 1e-4 * scale + 1e-6, (n, err, scale)
+
+
+@pytest.mark.parametrize("shape", [((2, 3, 1, 1), (6, 20)), ((2, 3, 6, 20), (12, 40)), ((2, 1, 24, 80), (48, 160)),
+                                   ((2, 2, 32, 64), (8, 16)), ((1, 3, 7, 9), (7, 9)), ((2, 3, 10, 12), (25, 31))])
+@pytest.mark.parametrize("sig", [False, True])
+def test_resize_bilinear(shape, sig):
+    from dd_b200.functional import resize_bilinear
+
+    ishape, size = shape
+    x = torch.randn(*ishape, device="cuda", requires_grad=True)
+    go = torch.randn(*ishape[:2], *size, device="cuda")
+    out = resize_bilinear(x, size, sigmoid=sig)
+    out.backward(go)
+    g1 = x.grad.clone()
+    x.grad = None
+    ref = F.interpolate(x, size, mode="bilinear", align_corners=False)
+    if sig:
+        ref = torch.sigmoid(ref)
+    ref.backward(go)
+    assert (out - ref).abs().max().item() <= 1e-5
+    assert (g1 - x.grad).abs().max().item() <= 1e-4 * (x.grad.abs().max().item() + 1e-9)
