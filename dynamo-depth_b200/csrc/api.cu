@@ -1,5 +1,7 @@
 // extern "C" surface of libdynamo_b200.so (see include/dynamo_b200.h).
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "dd_common.cuh"
@@ -7,6 +9,10 @@
 namespace dd {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches += n; }
+long long launches() { return g_launches.load(); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -46,6 +52,8 @@ extern "C" {
 const char* dd_last_error(void) { return dd::g_err; }
 
 int dd_version(void) { return 100; }
+
+long long dd_launch_count(void) { return dd::launches(); }
 
 int dd_device_sm_count(void) {
   int dev = 0, n = 0;

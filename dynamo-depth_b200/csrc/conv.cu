@@ -225,14 +225,21 @@ struct RouteArgs {
 };
 
 __device__ __forceinline__ float folded(const RouteArgs& a, const float* __restrict__ plane, int y, int x) {
-  // sum over the padded positions that ReflectionPad2d(1) maps onto (y, x)
+  // sum over the padded positions that ReflectionPad2d(1) maps onto (y, x): itself, -1 when the
+  // coordinate is 1, size when it is size-2 (both for size == 3)
+  int ys[3], xs[3];
+  int ny = 0, nx = 0;
+  ys[ny++] = y;
+  xs[nx++] = x;
+  if (a.reflect) {
+    if (y == 1) ys[ny++] = -1;
+    if (y == a.H - 2) ys[ny++] = a.H;
+    if (x == 1) xs[nx++] = -1;
+    if (x == a.W - 2) xs[nx++] = a.W;
+  }
   float s = 0.f;
-  const int ys[2] = {y, y == 1 ? -1 : (y == a.H - 2 ? a.H : y)};
-  const int xs[2] = {x, x == 1 ? -1 : (x == a.W - 2 ? a.W : x)};
-  const int ny = (a.reflect && ys[1] != y) ? 2 : 1, nx = (a.reflect && xs[1] != x) ? 2 : 1;
   for (int i = 0; i < ny; ++i)
     for (int j = 0; j < nx; ++j) s += __ldg(plane + (size_t)(ys[i] + a.off) * a.Wp + xs[j] + a.off);
-  if (a.reflect && a.H == 3 && y == 1) s += 0.f;   // H >= 4 on this path (decoder maps are >= 6x20)
   return s;
 }
 
@@ -401,7 +408,7 @@ static int validate_conv(const dd_conv_desc* d) {
   DD_REQUIRE(d->up0 >= 0 && d->up0 <= 2 && d->act >= 0 && d->act <= 3, "dd_conv: bad up0/act");
   DD_REQUIRE(d->up0 == DD_UP_NONE || (d->H % 2 == 0 && d->W % 2 == 0), "dd_conv: x2 up-sampling needs even H, W");
   DD_REQUIRE(!(d->residual && d->act != DD_ACT_NONE), "dd_conv: residual is only supported with DD_ACT_NONE");
-  DD_REQUIRE(!(d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT && (d->H < 4 || d->W < 4)), "dd_conv: reflect pad needs H, W >= 4");
+  DD_REQUIRE(!(d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT && (d->H < 2 || d->W < 2)), "dd_conv: reflect pad needs H, W >= 2");
   return DD_OK;
 }
 
@@ -420,10 +427,10 @@ template <int KS>
 static void launch_core(const ConvArgs& args, int cpt, dim3 grid_base, cudaStream_t st) {
   dim3 grid = grid_base;
   grid.y = (args.Cout + 8 * cpt - 1) / (8 * cpt);
-  if (cpt == 8) conv_core_kernel<KS, 8><<<grid, CONV_THREADS, 0, st>>>(args);
-  else if (cpt == 4) conv_core_kernel<KS, 4><<<grid, CONV_THREADS, 0, st>>>(args);
-  else if (cpt == 2) conv_core_kernel<KS, 2><<<grid, CONV_THREADS, 0, st>>>(args);
-  else conv_core_kernel<KS, 1><<<grid, CONV_THREADS, 0, st>>>(args);
+  if (cpt == 8) { conv_core_kernel<KS, 8><<<grid, CONV_THREADS, 0, st>>>(args); dd::count_launches(1); }
+  else if (cpt == 4) { conv_core_kernel<KS, 4><<<grid, CONV_THREADS, 0, st>>>(args); dd::count_launches(1); }
+  else if (cpt == 2) { conv_core_kernel<KS, 2><<<grid, CONV_THREADS, 0, st>>>(args); dd::count_launches(1); }
+  else { conv_core_kernel<KS, 1><<<grid, CONV_THREADS, 0, st>>>(args); dd::count_launches(1); }
 }
 
 static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose,
@@ -433,7 +440,7 @@ static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, 
   args.cout_pad = round_up(args.Cout, 8 * cpt);
   const size_t wn = (size_t)args.Cin * KK * args.cout_pad;
   conv_prep_weights_kernel<<<(int)((wn + 255) / 256 < 592 ? (wn + 255) / 256 : 592), 256, 0, st>>>(
-      w_oihw, wt_buf, Cout_f, Cin_f, KK, args.cout_pad, transpose ? 1 : 0);
+      w_oihw, wt_buf, Cout_f, Cin_f, KK, args.cout_pad, transpose ? 1 : 0); dd::count_launches(1);
   args.wt = wt_buf;
   args.tiles_x = (args.Wo + CT_W - 1) / CT_W;
   const int tiles_y = (args.Ho + CT_H - 1) / CT_H;
@@ -498,10 +505,10 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
   const float* g = grad_out;
   if (d->act != DD_ACT_NONE) {
     float* gc = reinterpret_cast<float*>((char*)workspace + ws.gconv);
-    conv_act_grad_kernel<<<(int)((n_out + 255) / 256 < 2368 ? (n_out + 255) / 256 : 2368), 256, 0, st>>>(grad_out, out, gc, n_out, d->act);
+    conv_act_grad_kernel<<<(int)((n_out + 255) / 256 < 2368 ? (n_out + 255) / 256 : 2368), 256, 0, st>>>(grad_out, out, gc, n_out, d->act); dd::count_launches(1);
     g = gc;
   }
-  if (grad_bias) conv_bias_grad_kernel<<<d->Cout, 256, 0, st>>>(g, grad_bias, d->B, d->Cout, d->H * d->W);
+  if (grad_bias) { conv_bias_grad_kernel<<<d->Cout, 256, 0, st>>>(g, grad_bias, d->B, d->Cout, d->H * d->W); dd::count_launches(1); }
   if (grad_weight) {
     DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));
     WgradArgs wa;
@@ -516,8 +523,8 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     wa.items_per_split = (n_items + splits - 1) / splits;
     splits = (n_items + wa.items_per_split - 1) / wa.items_per_split;
     dim3 grid(gx, gy, splits);
-    if (d->ksize == 3) conv_wgrad_kernel<3><<<grid, CONV_THREADS, 0, st>>>(wa);
-    else conv_wgrad_kernel<1><<<grid, CONV_THREADS, 0, st>>>(wa);
+    if (d->ksize == 3) { conv_wgrad_kernel<3><<<grid, CONV_THREADS, 0, st>>>(wa); dd::count_launches(1); }
+    else { conv_wgrad_kernel<1><<<grid, CONV_THREADS, 0, st>>>(wa); dd::count_launches(1); }
   }
   if (grad_x0 || grad_x1) {
     const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
@@ -542,7 +549,7 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     ra.H0 = d->up0 == DD_UP_NONE ? d->H : d->H / 2, ra.W0 = d->up0 == DD_UP_NONE ? d->W : d->W / 2;
     ra.gx0 = grad_x0, ra.gx1 = d->C1 > 0 ? grad_x1 : nullptr;
     const size_t n = (grad_x0 ? (size_t)d->B * d->C0 * ra.H0 * ra.W0 : 0) + (ra.gx1 ? (size_t)d->B * d->C1 * d->H * d->W : 0);
-    if (n > 0) conv_route_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(ra);
+    if (n > 0) { conv_route_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(ra); dd::count_launches(1); }
   }
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
@@ -627,7 +634,7 @@ int dd_resize_bilinear_fwd(const float* x, int BC, int h_in, int w_in, int h_out
   DD_REQUIRE(x && out && BC > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0, "dd_resize_bilinear_fwd: bad arguments");
   const size_t n = (size_t)BC * h_out * w_out;
   resize_fwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, (cudaStream_t)stream>>>(
-      x, out, BC, h_in, w_in, h_out, w_out, sigmoid);
+      x, out, BC, h_in, w_in, h_out, w_out, sigmoid); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
@@ -641,7 +648,7 @@ int dd_resize_bilinear_bwd(const float* grad_out, const float* out, int BC, int 
   DD_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)BC * h_in * w_in * sizeof(float), st));
   const size_t n = (size_t)BC * h_out * w_out;
   resize_bwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(grad_out, out, grad_x, BC, h_in,
-                                                                                            w_in, h_out, w_out, sigmoid);
+                                                                                            w_in, h_out, w_out, sigmoid); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }

@@ -9,6 +9,7 @@
 namespace dd {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // bookkeeping for dd_launch_count() (bench.py reports it)
 
 #define DD_CHECK_CUDA(expr)                                                                      \
   do {                                                                                           \

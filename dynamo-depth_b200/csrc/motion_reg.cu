@@ -96,8 +96,8 @@ int dd_msparsity_fwd(const float* mag, const float* mag_sum, const float* prob, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
-  msparsity_fwd_kernel<<<dim3(MS_CHUNKS, B), MS_THREADS, 0, st>>>(mag, mag_sum, prob, B, h * w, partial);
-  msparsity_finalize_kernel<<<1, 32, 0, st>>>(partial, B, out);
+  msparsity_fwd_kernel<<<dim3(MS_CHUNKS, B), MS_THREADS, 0, st>>>(mag, mag_sum, prob, B, h * w, partial); dd::count_launches(1);
+  msparsity_finalize_kernel<<<1, 32, 0, st>>>(partial, B, out); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
@@ -108,7 +108,7 @@ int dd_msparsity_bwd(const float* mag, const float* mag_sum, const float* prob, 
   DD_REQUIRE(mag && mag_sum && prob && out && grad_out && grad_prob && B > 0 && h > 0 && w > 0, "dd_msparsity_bwd: bad arguments");
   const size_t n = (size_t)B * h * w;
   const int blocks = (int)((n + MS_THREADS - 1) / MS_THREADS < 1184 ? (n + MS_THREADS - 1) / MS_THREADS : 1184);
-  msparsity_bwd_kernel<<<blocks, MS_THREADS, 0, (cudaStream_t)stream>>>(mag, mag_sum, prob, out, grad_out, B, h * w, grad_prob);
+  msparsity_bwd_kernel<<<blocks, MS_THREADS, 0, (cudaStream_t)stream>>>(mag, mag_sum, prob, out, grad_out, B, h * w, grad_prob); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }

@@ -207,9 +207,9 @@ int smooth_fwd_impl(const dd_smooth_task* tasks, int ntasks, float* sums, void* 
   int rc = fill_args(args, tasks, ntasks, workspace, bytes, any_norm);
   if (rc != DD_OK) return rc;
   DD_REQUIRE(sums != nullptr, "dd_smooth_fwd: sums is NULL");
-  if (any_norm) smooth_mean_kernel<<<dim3(args.maxBC, 1, ntasks), SM_THREADS, 0, st>>>(args);
-  smooth_fwd_kernel<<<dim3(SM_CHUNKS, args.maxB, ntasks), SM_THREADS, 0, st>>>(args);
-  smooth_finalize_kernel<<<ntasks * 2, 256, 0, st>>>(args.partial, sums, args.maxB * SM_CHUNKS);
+  if (any_norm) { smooth_mean_kernel<<<dim3(args.maxBC, 1, ntasks), SM_THREADS, 0, st>>>(args); dd::count_launches(1); }
+  smooth_fwd_kernel<<<dim3(SM_CHUNKS, args.maxB, ntasks), SM_THREADS, 0, st>>>(args); dd::count_launches(1);
+  smooth_finalize_kernel<<<ntasks * 2, 256, 0, st>>>(args.partial, sums, args.maxB * SM_CHUNKS); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
@@ -222,9 +222,9 @@ int smooth_bwd_impl(const dd_smooth_task* tasks, int ntasks, const float* grad_s
   if (rc != DD_OK) return rc;
   DD_REQUIRE(grad_sums != nullptr, "dd_smooth_bwd: grad_sums is NULL");
   args.grad_sums = grad_sums;
-  if (any_norm) smooth_mean_kernel<<<dim3(args.maxBC, 1, ntasks), SM_THREADS, 0, st>>>(args);
-  smooth_bwd_kernel<<<dim3(SM_CHUNKS, args.maxB, ntasks), SM_THREADS, 0, st>>>(args);
-  if (any_norm) smooth_bwd_norm_kernel<<<dim3(SM_CHUNKS, args.maxB, ntasks), SM_THREADS, 0, st>>>(args);
+  if (any_norm) { smooth_mean_kernel<<<dim3(args.maxBC, 1, ntasks), SM_THREADS, 0, st>>>(args); dd::count_launches(1); }
+  smooth_bwd_kernel<<<dim3(SM_CHUNKS, args.maxB, ntasks), SM_THREADS, 0, st>>>(args); dd::count_launches(1);
+  if (any_norm) { smooth_bwd_norm_kernel<<<dim3(SM_CHUNKS, args.maxB, ntasks), SM_THREADS, 0, st>>>(args); dd::count_launches(1); }
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }

@@ -568,7 +568,7 @@ static int launch_bwd(const BwdArgs& args, dim3 grid, cudaStream_t st) {
   auto kern = warp_photo_bwd_kernel<MODE, F>;
   const size_t smem_bytes = SM_TOTAL * sizeof(float);
   DD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  kern<<<grid, WP_THREADS, smem_bytes, st>>>(args);
+  kern<<<grid, WP_THREADS, smem_bytes, st>>>(args); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
@@ -622,7 +622,7 @@ int warp_photo_bwd_impl(const dd_warp_desc* desc, const float* grad_sums, const 
   if (rc != DD_OK) return rc;
   if (grads->T[0] || grads->T[1]) {
     finalize_T_kernel<<<desc->B, 32, 0, st>>>(args.partial_T, grads->T[0], F > 1 ? grads->T[1] : nullptr,
-                                              (int)(grid.x * grid.y));
+                                              (int)(grid.x * grid.y)); dd::count_launches(1);
     DD_CHECK_CUDA(cudaGetLastError());
   }
   return DD_OK;

@@ -334,7 +334,7 @@ template <int MODE, int F>
 static int launch_fwd(const FwdArgs& args, dim3 grid, size_t smem_bytes, cudaStream_t st) {
   auto kern = warp_photo_fwd_kernel<MODE, F>;
   DD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  kern<<<grid, WP_THREADS, smem_bytes, st>>>(args);
+  kern<<<grid, WP_THREADS, smem_bytes, st>>>(args); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
@@ -369,7 +369,7 @@ int warp_photo_fwd_impl(const dd_warp_desc* desc, const dd_warp_aux* aux, float*
   else if (mode == 1 && F == 1) rc = launch_fwd<1, 1>(args, grid, smem_bytes, st);
   else rc = launch_fwd<2, 1>(args, grid, smem_bytes, st);
   if (rc != DD_OK) return rc;
-  finalize_sums_kernel<<<desc->num_scales * DD_NSUM, 256, 0, st>>>(args.partial, sums, num_ctas, 6);
+  finalize_sums_kernel<<<desc->num_scales * DD_NSUM, 256, 0, st>>>(args.partial, sums, num_ctas, 6); dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }

@@ -92,6 +92,7 @@ SIGNATURES = {
     "dd_last_error": (C.c_char_p, []),
     "dd_version": (C.c_int, []),
     "dd_device_sm_count": (C.c_int, []),
+    "dd_launch_count": (C.c_longlong, []),
     "dd_warp_photo_workspace_bytes": (C.c_size_t, [C.POINTER(WarpDesc)]),
     "dd_warp_photo_fwd": (C.c_int, [C.POINTER(WarpDesc), C.POINTER(WarpAux), FP, FP, C.c_size_t, FP]),
     "dd_warp_photo_bwd": (C.c_int, [C.POINTER(WarpDesc), FP, C.POINTER(WarpAux), C.POINTER(WarpGrads), FP, C.c_size_t, FP]),
@@ -106,6 +107,12 @@ SIGNATURES = {
     "dd_conv_bwd": (C.c_int, [C.POINTER(ConvDesc), FP, FP, FP, FP, FP, FP, FP, C.c_size_t, FP]),
     "dd_resize_bilinear_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_resize_bilinear_bwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_backproject_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_backproject_bwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_project_fwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
+    "dd_project_bwd": (C.c_int, [FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
+    "dd_ssim_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_ssim_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
 }
 
 _lib = None

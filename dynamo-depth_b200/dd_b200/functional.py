@@ -34,6 +34,28 @@ class WarpConfig:
                (L.DD_FLAG_AUTOMASK if self.automask else 0)
 
 
+# optional CUDA-event timers around individual C-ABI calls (bench.py's roofline leg):
+# KERNEL_TIMERS[name] = list of (start_event, end_event) while enabled, None otherwise
+KERNEL_TIMERS = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_TIMERS is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if KERNEL_TIMERS is not None:
+            self.ev[1].record()
+            KERNEL_TIMERS.setdefault(self.name, []).append(self.ev)
+        return False
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -135,8 +157,9 @@ class _ViewSynthesisFn(torch.autograd.Function):
         sums = torch.empty(S, L.DD_NSUM, device=dev)
         ws_bytes = lib.dd_warp_photo_workspace_bytes(C.byref(desc))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        L.check(lib.dd_warp_photo_fwd(C.byref(desc), C.byref(aux), sums.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
-                "dd_warp_photo_fwd")
+        with _timed("warp_photo_fwd"):
+            L.check(lib.dd_warp_photo_fwd(C.byref(desc), C.byref(aux), sums.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+                    "dd_warp_photo_fwd")
 
         ctx.cfg, ctx.nF = cfg, nF
         ctx.save_for_backward(*tensors)
@@ -205,8 +228,9 @@ class _ViewSynthesisFn(torch.autograd.Function):
         gs = grad_sums.contiguous().float()
         ws_bytes = lib.dd_warp_photo_workspace_bytes(C.byref(desc))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        L.check(lib.dd_warp_photo_bwd(C.byref(desc), gs.data_ptr(), C.byref(saved), C.byref(g), ws.data_ptr(), ws_bytes,
-                                      _stream()), "dd_warp_photo_bwd")
+        with _timed("warp_photo_bwd"):
+            L.check(lib.dd_warp_photo_bwd(C.byref(desc), gs.data_ptr(), C.byref(saved), C.byref(g), ws.data_ptr(), ws_bytes,
+                                          _stream()), "dd_warp_photo_bwd")
         for idx in range(len(grads)):
             if not need[idx]:
                 grads[idx] = None
@@ -457,3 +481,102 @@ def resize_bilinear(x, size, sigmoid=False):
     if not x.is_cuda:
         raise L.DynamoB200Error("resize_bilinear needs CUDA tensors (no CPU fallback)")
     return _ResizeFn.apply(_prep(x), (int(size[0]), int(size[1])), bool(sigmoid))
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone geometry / SSIM layers (tools.py:167-257) -- module surface for eval / user code
+# ---------------------------------------------------------------------------------------------
+
+
+class _BackprojectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K):
+        lib = L.load()
+        B, _, H, W = depth.shape
+        pts = torch.empty(B, 4, H * W, device=depth.device)
+        L.check(lib.dd_backproject_fwd(L.ptr(depth), L.ptr(inv_K), B, H, W, pts.data_ptr(), _stream()), "dd_backproject_fwd")
+        ctx.save_for_backward(inv_K)
+        ctx.dims = (B, H, W)
+        return pts
+
+    @staticmethod
+    def backward(ctx, gpts):
+        lib = L.load()
+        (inv_K,) = ctx.saved_tensors
+        B, H, W = ctx.dims
+        gd = torch.empty(B, 1, H, W, device=gpts.device)
+        L.check(lib.dd_backproject_bwd(gpts.contiguous().data_ptr(), inv_K.data_ptr(), B, H, W, gd.data_ptr(), _stream()),
+                "dd_backproject_bwd")
+        return gd, None
+
+
+def backproject(depth, inv_K):
+    if not depth.is_cuda:
+        raise L.DynamoB200Error("backproject needs CUDA tensors (no CPU fallback)")
+    return _BackprojectFn.apply(_prep(depth), _prep(inv_K))
+
+
+class _ProjectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, K, T, H, W):
+        lib = L.load()
+        B = points.shape[0]
+        pix = torch.empty(B, H, W, 2, device=points.device)
+        ego = torch.empty(B, 3, H * W, device=points.device)
+        L.check(lib.dd_project_fwd(L.ptr(points), L.ptr(K), L.ptr(T), B, H, W, pix.data_ptr(), ego.data_ptr(), _stream()),
+                "dd_project_fwd")
+        ctx.save_for_backward(points, K, T)
+        ctx.dims = (B, H, W)
+        return pix, ego
+
+    @staticmethod
+    def backward(ctx, gpix, gego):
+        lib = L.load()
+        points, K, T = ctx.saved_tensors
+        B, H, W = ctx.dims
+        gp = torch.empty_like(points)
+        gT = torch.empty(B, 4, 4, device=points.device) if (T is not None and ctx.needs_input_grad[2]) else None
+        p = lambda t: t.contiguous().data_ptr() if t is not None else None
+        L.check(lib.dd_project_bwd(points.data_ptr(), K.data_ptr(), p(T), p(gpix), p(gego), B, H, W, gp.data_ptr(), p(gT),
+                                   _stream()), "dd_project_bwd")
+        return gp, None, gT, None, None
+
+
+def project3d(points, K, T, H, W):
+    if not points.is_cuda:
+        raise L.DynamoB200Error("project3d needs CUDA tensors (no CPU fallback)")
+    return _ProjectFn.apply(_prep(points), _prep(K), _prep(T), int(H), int(W))
+
+
+class _SsimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        lib = L.load()
+        H, W = x.shape[-2:]
+        BC = x.numel() // (H * W)
+        out = torch.empty_like(x)
+        L.check(lib.dd_ssim_fwd(x.data_ptr(), y.data_ptr(), BC, H, W, out.data_ptr(), _stream()), "dd_ssim_fwd")
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        lib = L.load()
+        x, y = ctx.saved_tensors
+        H, W = x.shape[-2:]
+        BC = x.numel() // (H * W)
+        go = go.contiguous()
+        gx = gy = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            L.check(lib.dd_ssim_bwd(x.data_ptr(), y.data_ptr(), go.data_ptr(), BC, H, W, gx.data_ptr(), _stream()), "dd_ssim_bwd")
+        if ctx.needs_input_grad[1]:   # SSIM(x, y) is symmetric in its arguments
+            gy = torch.empty_like(y)
+            L.check(lib.dd_ssim_bwd(y.data_ptr(), x.data_ptr(), go.data_ptr(), BC, H, W, gy.data_ptr(), _stream()), "dd_ssim_bwd")
+        return gx, gy
+
+
+def ssim(x, y):
+    if not x.is_cuda:
+        raise L.DynamoB200Error("ssim needs CUDA tensors (no CPU fallback)")
+    return _SsimFn.apply(_prep(x), _prep(y))

@@ -1,0 +1,64 @@
+"""ResNet encoders (reference: networks/resnet_encoder.py).  Kept in PyTorch/cuDNN on purpose: the
+north-star reserves the tensor cores for these contractions and hand-writes only the decoders and the
+loss path.  state_dict keys are torchvision's under the attribute `encoder` (including the unused
+`encoder.fc.*`), so reference checkpoints load unchanged."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torchvision.models as tvm
+
+_FACTORIES = {18: (tvm.resnet18, "ResNet18_Weights"), 34: (tvm.resnet34, "ResNet34_Weights"),
+              50: (tvm.resnet50, "ResNet50_Weights"), 101: (tvm.resnet101, "ResNet101_Weights"),
+              152: (tvm.resnet152, "ResNet152_Weights")}
+
+
+def _imagenet_state(num_layers):
+    factory, weights_name = _FACTORIES[num_layers]
+    weights = getattr(tvm, weights_name).IMAGENET1K_V1
+    return weights.get_state_dict(progress=False)   # needs network access or a populated torch hub cache
+
+
+def resnet_multiimage_input(num_layers, pretrained=False, num_input_images=1, inp_disp=False):
+    """ResNet-18/50 whose stem takes `num_input_images` stacked frames (resnet_encoder.py:64-92)."""
+    assert num_layers in (18, 50), "Can only run with 18 or 50 layer resnet"
+    per_img = 4 if inp_disp else 3
+    net = _FACTORIES[num_layers][0](weights=None)
+    stem = nn.Conv2d(num_input_images * per_img, 64, kernel_size=7, stride=2, padding=3, bias=False)
+    nn.init.kaiming_normal_(stem.weight, mode="fan_out", nonlinearity="relu")
+    net.conv1 = stem
+    if pretrained:
+        state = _imagenet_state(num_layers)
+        w = nn.init.kaiming_normal_(torch.ones(64, per_img * num_input_images, 7, 7))
+        for k in range(num_input_images):   # tile the RGB stem over the frames, keep the average response
+            w[:, per_img * k:per_img * k + 3] = state["conv1.weight"] / num_input_images
+        state["conv1.weight"] = w
+        net.load_state_dict(state)
+    return net
+
+
+class ResnetEncoder(nn.Module):
+    def __init__(self, num_layers, pretrained, num_input_images=1, inp_disp=False):
+        super().__init__()
+        if num_layers not in _FACTORIES:
+            raise ValueError(f"{num_layers} is not a valid number of resnet layers")
+        self.num_ch_enc = np.array([64, 64, 128, 256, 512])
+        if num_input_images == 1:
+            assert not inp_disp, "single input image cannot be RGBD"
+            self.encoder = _FACTORIES[num_layers][0](weights=None)
+            if pretrained:
+                self.encoder.load_state_dict(_imagenet_state(num_layers))
+        else:
+            self.encoder = resnet_multiimage_input(num_layers, pretrained, num_input_images, inp_disp)
+        if num_layers > 34:
+            self.num_ch_enc[1:] *= 4
+
+    def forward(self, input_image):
+        e = self.encoder
+        x = e.relu(e.bn1(e.conv1((input_image - 0.45) / 0.225)))
+        self.features = [x]
+        x = e.layer1(e.maxpool(x))
+        self.features.append(x)
+        for layer in (e.layer2, e.layer3, e.layer4):
+            x = layer(x)
+            self.features.append(x)
+        return self.features

@@ -51,6 +51,8 @@ const char* dd_last_error(void);
 int dd_version(void);
 /* number of SMs / device index the library sees (negative on error) */
 int dd_device_sm_count(void);
+/* number of kernels this library has launched in this process so far (bookkeeping for benchmarks) */
+long long dd_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Fused view synthesis + photometric loss
@@ -205,6 +207,25 @@ int dd_resize_bilinear_fwd(const float* x, int BC, int h_in, int w_in, int h_out
 /* grad_x (BC,h_in,w_in) overwritten; `out` is the forward result (needed when sigmoid != 0) */
 int dd_resize_bilinear_bwd(const float* grad_out, const float* out, int BC, int h_in, int w_in, int h_out, int w_out,
                            int sigmoid, float* grad_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone geometry / photometric layers (the module surface eval scripts and user code call:
+ * trainer.backproject_depth[s](depth, inv_K), trainer.project_3d[s](points, K, T), SSIM()(x, y)).
+ * The training step itself goes through dd_warp_photo_* and never materialises these tensors.
+ * ------------------------------------------------------------------------------------------ */
+/* tools.BackprojectDepth.forward (tools.py:191-197): points (B,4,H*W) = cat(depth * inv_K[:3,:3] @ (u,v,1), 1) */
+int dd_backproject_fwd(const float* depth, const float* inv_K, int B, int H, int W, float* points, void* stream);
+int dd_backproject_bwd(const float* grad_points, const float* inv_K, int B, int H, int W, float* grad_depth, void* stream);
+/* tools.Project3D.forward (tools.py:211-224): pix (B,H,W,2) normalised to [-1,1], ego (B,3,H*W); T may be NULL */
+int dd_project_fwd(const float* points, const float* K, const float* T, int B, int H, int W, float* pix, float* ego,
+                   void* stream);
+/* grad_pix / grad_ego may be NULL (treated as zero); grad_points (B,4,H*W) and grad_T (B,4,4, may be NULL) overwritten */
+int dd_project_bwd(const float* points, const float* K, const float* T, const float* grad_pix, const float* grad_ego, int B,
+                   int H, int W, float* grad_points, float* grad_T, void* stream);
+/* tools.SSIM.forward (tools.py:243-257): out (B,C,H,W) = clamp((1 - SSIM(x,y)) / 2, 0, 1) */
+int dd_ssim_fwd(const float* x, const float* y, int BC, int H, int W, float* out, void* stream);
+/* gradient w.r.t. x (SSIM is symmetric: swap x and y for the gradient w.r.t. y) */
+int dd_ssim_bwd(const float* x, const float* y, const float* grad_out, int BC, int H, int W, float* grad_x, void* stream);
 
 #ifdef __cplusplus
 }

@@ -133,3 +133,40 @@ def add_color_pyramid(inputs, scales, height, width):
             rs = T.Resize((height // 2**s, width // 2**s), interpolation=T.InterpolationMode.BICUBIC, antialias=True)
             inputs[("color", 0, s)] = torch.clamp(rs(inputs[("color", 0, s - 1)]), 0, 1)
     return inputs
+
+
+def fill_state(module_or_state, seed):
+    """Deterministic, key-addressed parameter fill shared by the reference, the oracle and the product
+    (no weight files ship): every tensor is drawn from its own generator seeded by crc32(key)."""
+    import zlib
+
+    sd = module_or_state.state_dict() if hasattr(module_or_state, "state_dict") else module_or_state
+    out = {}
+    for key in sorted(sd.keys()):
+        t = sd[key]
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2**31 - 1))
+        leaf = key.split(".")[-1]
+        if not torch.is_tensor(t):
+            out[key] = t
+        elif leaf == "num_batches_tracked":
+            out[key] = torch.zeros_like(t)
+        elif leaf == "running_mean":
+            out[key] = 0.1 * torch.randn(t.shape, generator=g)
+        elif leaf == "running_var":
+            out[key] = 0.8 + 0.4 * torch.rand(t.shape, generator=g)
+        elif leaf in ("gamma", "gamma_xca"):
+            out[key] = 0.2 * torch.randn(t.shape, generator=g)
+        elif leaf == "temperature":
+            out[key] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        elif leaf == "bias":
+            out[key] = 0.05 * torch.randn(t.shape, generator=g)
+        elif t.dim() >= 2:
+            fan_in = t[0].numel()
+            out[key] = torch.randn(t.shape, generator=g) * (1.6 / fan_in) ** 0.5
+        else:  # 1-D scale of a normalisation layer
+            out[key] = 1.0 + 0.1 * torch.randn(t.shape, generator=g)
+        if torch.is_tensor(out[key]):
+            out[key] = out[key].to(t.dtype)
+    if hasattr(module_or_state, "load_state_dict"):
+        module_or_state.load_state_dict(out)
+    return out

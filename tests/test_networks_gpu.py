@@ -1,0 +1,152 @@
+"""GPU parity of the product's decoders / Model / Trainer step (hand-written kernels) against goldens
+recorded from the unmodified reference.  Tolerance 1e-4 relative fp32 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets_io, synth
+from oracle.golden_io import parse_key
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _run_product(tag):
+    from networks.layers import transformation_from_parameters
+
+    m = nets_io.product_decoder(tag).cuda()
+    if tag in ("md2", "lite"):
+        feats = [f.cuda().requires_grad_(True) for f in nets_io.decoder_inputs(tag)]
+        out, ins = m(feats), feats
+    elif tag in ("flow", "mask"):
+        feats = [f.cuda().requires_grad_(True) for f in nets_io.decoder_inputs("motion")]
+        ego = nets_io.seeded((nets_io.DEC_B, 6, 1, 1), 500, 0.01).cuda().requires_grad_(True)
+        out, ins = m(feats, ego), feats + [ego]
+    else:
+        feats = [f.cuda().requires_grad_(True) for f in nets_io.decoder_inputs("pose")]
+        aa, tr = m([feats])
+        T = transformation_from_parameters(aa[:, 0] * 30, tr[:, 0] * 30, invert=True)
+        out, ins = {"axisangle": aa, "translation": tr, "T": T}, feats
+    nets_io.objective(out).backward()
+    return m, out, ins
+
+
+@pytest.mark.parametrize("tag", ["md2", "lite", "flow", "mask", "pose"])
+def test_decoders_match_reference(tag):
+    z = nets_io.load_npz("nets_decoders")
+    m, out, ins = _run_product(tag)
+    ref = nets_io.golden_outputs(z, tag)
+    for k, v in ref.items():
+        assert (out[k].detach().cpu() - v).abs().max().item() <= 1e-4 * (1e-2 + v.abs().max().item()), (tag, k)
+    for n, t in enumerate(ins):
+        g = torch.from_numpy(z[f"{tag}:gin:{n}"])
+        assert (t.grad.cpu() - g).abs().max().item() <= 1e-4 * (g.abs().max().item() + 1e-9), (tag, "gin", n)
+    params = dict(m.named_parameters())
+    checked = 0
+    for k in z.files:
+        if k.startswith(f"{tag}:gparam:"):
+            name = k[len(f"{tag}:gparam:"):]
+            g = torch.from_numpy(z[k])
+            assert (params[name].grad.cpu() - g).abs().max().item() <= 1e-4 * (g.abs().max().item() + 1e-9), (tag, name)
+            checked += 1
+        if k.startswith(f"{tag}:gchk:"):
+            name = k[len(f"{tag}:gchk:"):]
+            assert np.allclose(nets_io.chk(params[name].grad), z[k], rtol=3e-4, atol=1e-6), (tag, name)
+            checked += 1
+    assert checked > 4
+
+
+def _product_model(dm, H, W, B, seed, extra=()):
+    import networks
+    import options
+
+    opt = options.DynamoOptions().parse(args=["-d", "kitti", "--depth_model", dm, "--weights_init", "scratch", "-b", str(B),
+                                              "--height", str(H), "--width", str(W)] + list(extra))
+    model = networks.Model(opt)
+    synth.fill_state(model, seed)
+    return opt, model.cuda()
+
+
+@pytest.mark.parametrize("dm,name,seed", [("monodepthv2", "model_fwd_md2_64x96", 31), ("litemono", "model_fwd_lite_64x96", 32)])
+def test_model_forward_matches_reference(dm, name, seed):
+    z = nets_io.load_npz(name)
+    B, H, W = (int(v) for v in z["meta:shape"])
+    opt, model = _product_model(dm, H, W, B, seed)
+    model.set_eval()
+    inputs, _ = synth.make_loss_inputs(seed, B, H, W, opt.scales, flow=False)
+    inputs = {k: v.cuda() for k, v in inputs.items()}
+    with torch.no_grad():
+        out = model(inputs)
+    n = 0
+    for k in z.files:
+        if k.startswith("chk:"):
+            key = parse_key(k[4:])
+            if torch.is_tensor(out.get(key)):
+                assert np.allclose(nets_io.chk(out[key]), z[k], rtol=5e-4, atol=1e-5), (key, nets_io.chk(out[key]), z[k])
+                n += 1
+        if k.startswith("out:"):
+            key = parse_key(k[4:])
+            ref = torch.from_numpy(z[k])
+            assert (out[key].cpu() - ref).abs().max().item() <= 2e-4 * (1e-3 + ref.abs().max().item()), key
+    assert n >= 10
+
+
+def test_trainer_step_config1_tiny_kitti():
+    """BASELINE config 1: tiny_kitti 192x640 bs2 monodepthv2, phase disp_init, 1 step (fwd + loss + bwd + Adam)."""
+    import options
+    from Trainer import Trainer
+
+    z = nets_io.load_npz("step_config1_tiny_kitti")
+    opt = options.DynamoOptions().parse(args=["-d", "kitti", "--depth_model", "monodepthv2", "--weights_init", "scratch", "-b", "2"])
+    opt.ddp = False
+    tr = Trainer(opt)
+    synth.fill_state(tr.base_model, 21)
+    tr.setup_phase("disp_init")
+    tr.bool_automask = True
+    tr.step, tr.num_steps_per_epoch = 0, 100
+    tr.set_train()
+    tr.automask_noise = synth.automask_noise(21, 2, 192, 640, opt.scales)
+    inputs = {}
+    for f in (0, -1, 1):
+        img = torch.from_numpy(z[f"img:{f}"]).float() / 255
+        inputs[("color", f, 0)] = img.unsqueeze(0).repeat(2, 1, 1, 1)
+        inputs[("color_aug", f, 0)] = inputs[("color", f, 0)]
+    K = torch.from_numpy(z["K"]).unsqueeze(0).repeat(2, 1, 1)
+    inputs[("K", 0)] = K
+    inputs[("inv_K", 0)] = torch.from_numpy(np.linalg.pinv(z["K"])).unsqueeze(0).repeat(2, 1, 1)
+    for f in (-1, 1):
+        inputs[("ts", f)] = torch.ones(2, dtype=torch.int64)
+    outputs, losses = tr.process_batch(inputs)
+    losses["loss"].backward()
+    for k in z.files:
+        if k.startswith("loss:"):
+            got = losses[k[5:]]
+            got = float(got.detach()) if torch.is_tensor(got) else float(got)
+            assert got == pytest.approx(float(z[k]), rel=1e-4, abs=1e-7), (k, got, float(z[k]))
+    for s in opt.scales:
+        assert np.allclose(nets_io.chk(outputs[("disp", 0, s)]), z[f"chk:disp|0|{s}"], rtol=2e-4), s
+    for f in (-1, 1):
+        ref = torch.from_numpy(z[f"out:cam_T_cam|0|{f}"])
+        assert (outputs[("cam_T_cam", 0, f)].detach().cpu() - ref).abs().max().item() <= 1e-5
+    # gradients of every trained parameter (L2 norm via the checksum's third entry) and one Adam step
+    bad = []
+    for k in z.files:
+        if k.startswith("gchk:"):
+            mod, name = k[5:].split(".", 1)
+            p = dict(getattr(tr.base_model, mod).named_parameters())[name]
+            got, ref = nets_io.chk(p.grad), z[k]
+            if not np.isclose(got[2], ref[2], rtol=5e-3, atol=1e-12):
+                bad.append((k, got[2], ref[2]))
+    assert not bad, bad[:5]
+    tr.optim["optimizer"].step()
+    for k in z.files:
+        if k.startswith("pchk:"):
+            mod, name = k[5:].split(".", 1)
+            p = dict(getattr(tr.base_model, mod).named_parameters())[name]
+            assert np.allclose(nets_io.chk(p), z[k], rtol=1e-4, atol=1e-6), k
