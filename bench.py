@@ -206,6 +206,11 @@ def run_ours(args):
 
     # warm-up (cuDNN autotuning, allocator growth), then the device-resident timed region
     timed(resident, max(args.warmup, 3), False)
+    if args.profile_step:   # under `ncu --profile-from-start off`: capture exactly one training step
+        torch.cuda.profiler.start()
+        timed(resident, 1, False)
+        torch.cuda.profiler.stop()
+        return
     Fn.KERNEL_TIMERS = {}
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -285,6 +290,7 @@ def main():
     ap.add_argument("--phase", default="fine_tune", choices=["disp_init", "motion_init", "mask_init", "fine_tune"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around one step (for ncu), no JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

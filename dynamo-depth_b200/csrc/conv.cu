@@ -374,14 +374,17 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   }
 }
 
-// grad_bias[co] = sum over b, y, x of g
-__global__ void conv_bias_grad_kernel(const float* __restrict__ g, float* __restrict__ gb, int B, int Cout, int HW) {
+// grad_bias[co] = sum over b, y, x of g; grid (Cout, chunks), one atomicAdd per CTA into the zeroed output
+__global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __restrict__ g, float* __restrict__ gb, int B, int Cout,
+                                                             int HW) {
   __shared__ float sh[8];
   const int co = blockIdx.x;
+  const size_t per_img = (size_t)HW;
+  const size_t total = (size_t)B * per_img;
   float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float* p = g + ((size_t)b * Cout + co) * HW;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += __ldg(p + i);
+  for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.y * blockDim.x) {
+    const size_t b = i / per_img, p = i - b * per_img;
+    acc += __ldg(g + (b * Cout + co) * per_img + p);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -389,7 +392,7 @@ __global__ void conv_bias_grad_kernel(const float* __restrict__ g, float* __rest
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
-    gb[co] = t;
+    atomicAdd(gb + co, t);
   }
 }
 
@@ -508,7 +511,15 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     conv_act_grad_kernel<<<(int)((n_out + 255) / 256 < 2368 ? (n_out + 255) / 256 : 2368), 256, 0, st>>>(grad_out, out, gc, n_out, d->act); dd::count_launches(1);
     g = gc;
   }
-  if (grad_bias) { conv_bias_grad_kernel<<<d->Cout, 256, 0, st>>>(g, grad_bias, d->B, d->Cout, d->H * d->W); dd::count_launches(1); }
+  if (grad_bias) {
+    DD_CHECK_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d->Cout * sizeof(float), st));
+    const size_t total = (size_t)d->B * d->H * d->W;
+    int chunks = (int)((total + 256 * 8 - 1) / (256 * 8));              // >= 8 elements per thread
+    const int cap = (148 * 8 + d->Cout - 1) / d->Cout;                   // ~8 CTAs per SM over all channels
+    chunks = chunks < 1 ? 1 : (chunks > cap ? cap : chunks);
+    conv_bias_grad_kernel<<<dim3(d->Cout, chunks), 256, 0, st>>>(g, grad_bias, d->B, d->Cout, d->H * d->W);
+    dd::count_launches(1);
+  }
   if (grad_weight) {
     DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));
     WgradArgs wa;
