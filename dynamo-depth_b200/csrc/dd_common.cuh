@@ -59,6 +59,7 @@ __device__ __forceinline__ Taps up_taps(int dst, int shift, int n_in) {
 }
 
 __device__ __forceinline__ float bilerp(const float* __restrict__ p, int w, const Taps& ty, const Taps& tx) {
+  if (ty.i0 == ty.i1 && tx.i0 == tx.i1) return __ldg(p + ty.i0 * w + tx.i0);   // same-size level: plain copy
   const float v00 = __ldg(p + ty.i0 * w + tx.i0), v01 = __ldg(p + ty.i0 * w + tx.i1);
   const float v10 = __ldg(p + ty.i1 * w + tx.i0), v11 = __ldg(p + ty.i1 * w + tx.i1);
   return (1.f - ty.l) * ((1.f - tx.l) * v00 + tx.l * v01) + ty.l * ((1.f - tx.l) * v10 + tx.l * v11);

@@ -55,7 +55,7 @@ __global__ void project_fwd_kernel(const float* __restrict__ pts, const float* _
       X.w = t[12] * x + t[13] * y + t[14] * z + t[15] * w;
     }
     const Proj pr = project_K(K + b * 16, X);
-    reinterpret_cast<float2*>(pix)[i] = make_float2(normalise(pr.px, W), normalise(pr.py, H));
+    reinterpret_cast<float2*>(pix)[i] = make_float2(normalise(pr.px, 1.f / (float)(W - 1)), normalise(pr.py, 1.f / (float)(H - 1)));
     float* e = ego + (size_t)b * 3 * P + p;
     e[0] = X.x - x, e[P] = X.y - y, e[2 * P] = X.z - z;
   }

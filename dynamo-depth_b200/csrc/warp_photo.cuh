@@ -15,6 +15,7 @@ struct CamConst {
   float iK[9];      // inv_K[:3,:3]       (tools.py:193)
   float T[2][16];   // cam_T_cam per source frame
   float ts[2];      // ('ts', f)
+  float inv_wm1, inv_hm1;   // 1/(W-1), 1/(H-1) of Project3D's normalisation (tools.py:219-220)
 };
 
 __device__ __forceinline__ void load_cam(CamConst* cam, const dd_warp_desc& d, int b, int tid) {
@@ -30,6 +31,10 @@ __device__ __forceinline__ void load_cam(CamConst* cam, const dd_warp_desc& d, i
   if (tid >= 128 && tid < 128 + d.num_frames) {
     const int f = tid - 128;
     cam->ts[f] = d.ts[f] ? __ldg(d.ts[f] + b) : 1.f;
+  }
+  if (tid == 160) {
+    cam->inv_wm1 = 1.f / (float)(d.W - 1);
+    cam->inv_hm1 = 1.f / (float)(d.H - 1);
   }
 }
 
@@ -53,6 +58,7 @@ __device__ __forceinline__ Vec4 apply_T(const float* T, const Vec3& p) {
 // c = K[:3,:] @ X ; pix = c[:2] / (c[2] + eps)   (tools.py:214-216)
 struct Proj {
   float c0, c1, z;   // z = c2 + eps
+  float iz;          // 1 / z
   float px, py;      // pixel coordinates
 };
 __device__ __forceinline__ Proj project_K(const float* K, const Vec4& X) {
@@ -60,15 +66,17 @@ __device__ __forceinline__ Proj project_K(const float* K, const Vec4& X) {
   p.c0 = K[0] * X.x + K[1] * X.y + K[2] * X.z + K[3] * X.w;
   p.c1 = K[4] * X.x + K[5] * X.y + K[6] * X.z + K[7] * X.w;
   p.z = (K[8] * X.x + K[9] * X.y + K[10] * X.z + K[11] * X.w) + 1e-7f;
-  p.px = p.c0 / p.z;
-  p.py = p.c1 / p.z;
+  // one correctly rounded reciprocal + two multiplies instead of two divisions (<= 1.5 ulp from c/z)
+  p.iz = __frcp_rn(p.z);
+  p.px = p.c0 * p.iz;
+  p.py = p.c1 * p.iz;
   return p;
 }
 
 // normalised grid coordinate as Project3D stores it: (pix/(size-1) - 0.5) * 2   (tools.py:219-221)
-__device__ __forceinline__ float normalise(float pix, int size) { return (pix / (float)(size - 1) - 0.5f) * 2.f; }
+__device__ __forceinline__ float normalise(float pix, float inv_size_m1) { return (pix * inv_size_m1 - 0.5f) * 2.f; }
 // grid_sample(align_corners=True) un-normalisation: ((g+1)/2) * (size-1)   (GridSampler.cuh:23-30)
-__device__ __forceinline__ float unnormalise(float g, int size) { return ((g + 1.f) / 2.f) * (float)(size - 1); }
+__device__ __forceinline__ float unnormalise(float g, int size) { return ((g + 1.f) * 0.5f) * (float)(size - 1); }
 
 // Border-clamped bilinear sampling footprint (padding_mode='border', GridSampler.cuh:55-57)
 struct Foot {
@@ -137,8 +145,8 @@ __device__ __forceinline__ void frame_geometry(FrameGeom& g, const PixelGeom& pg
       const Proj pe = project_K(cam->K, Xe);
       const Vec4 Xc = {pg.Pc.x + cf_up.x, pg.Pc.y + cf_up.y, pg.Pc.z + cf_up.z, 1.f};   // Trainer.py:257-260
       const Proj pc = project_K(cam->K, Xc);
-      g.dsx = normalise(pe.px, W) - normalise(pc.px, W);
-      g.dsy = normalise(pe.py, H) - normalise(pc.py, H);
+      g.dsx = normalise(pe.px, cam->inv_wm1) - normalise(pc.px, cam->inv_wm1);
+      g.dsy = normalise(pe.py, cam->inv_hm1) - normalise(pc.py, cam->inv_hm1);
     }
     if (MODE == 2) {
       g.Pin = {pg.Pc.x + g.res.x * m_up, pg.Pc.y + g.res.y * m_up, pg.Pc.z + g.res.z * m_up};   // Trainer.py:265-267
@@ -149,8 +157,8 @@ __device__ __forceinline__ void frame_geometry(FrameGeom& g, const PixelGeom& pg
     }
   }
   g.pr = project_K(cam->K, g.X);
-  g.gx = normalise(g.pr.px, W);
-  g.gy = normalise(g.pr.py, H);
+  g.gx = normalise(g.pr.px, cam->inv_wm1);
+  g.gy = normalise(g.pr.py, cam->inv_hm1);
 }
 
 }  // namespace dd

@@ -1,17 +1,20 @@
 // Fused view synthesis + photometric loss, backward (dd_warp_photo_bwd).
 //
-// Recompute-based: nothing full-resolution is saved by the forward pass.  One CTA owns a 32x16
-// tile of one image and, per pyramid level,
-//   stage A  re-warps both source frames over the tile + 2-pixel halo (36x20) into shared memory;
-//   stage B  re-derives the 3x3 SSIM statistics, the candidate losses and the per-pixel argmin on
-//            the tile + 1-pixel halo (34x18) and stores, for the selected frame only, the three
-//            coefficient maps of d(loss)/d(mu_x, E[x^2], E[xy]);
+// One CTA owns a 32x16 tile of one image and, per pyramid level,
+//   stage A  stages the warped source frames over the tile + 2-pixel halo (36x20) in shared memory:
+//            read back from the forward pass' warped images when they were kept (SAVED, 24 B per
+//            pixel and level instead of ~600 instructions of geometry + 24 gathers), else re-warped;
+//   stage B  re-derives the 3x3 SSIM statistics with a register ring marching down each column of
+//            the tile + 1-pixel halo (34x18), the candidate losses and the per-pixel argmin, and
+//            stores, for the selected frame only, the three coefficient maps of
+//            d(loss)/d(mu_x, E[x^2], E[xy]);
 //   stage C  box-sums the coefficient maps (ReflectionPad2d fold-back = weight 2 on the rows /
 //            columns next to the border), adds the L1 term, re-gathers the four bilinear taps and
 //            chains through projection, pose, (scene flow, motion mask,) back-projection and
 //            disp->depth (appendix A.3); pose gradients are reduced per CTA;
-//   stage D  transposes the bilinear up-sampling of disp_s / flow_s / mask_s inside shared memory
-//            and flushes the low-resolution tile (plain stores at level 0, atomics above).
+//   stage D  transposes the bilinear up-sampling of disp_s / flow_s / mask_s separably (rows, then
+//            columns) inside shared memory and flushes the low-resolution tile (plain stores at
+//            level 0, atomics above).
 #include "warp_photo.cuh"
 
 namespace dd {
@@ -29,6 +32,7 @@ struct BwdArgs {
   dd_warp_desc d;
   dd_warp_grads g;
   const float* resid_saved[DD_MAX_SCALES][DD_MAX_FRAMES];
+  const float* warped_saved[DD_MAX_SCALES][DD_MAX_FRAMES];   // (B,3,H,W) from the forward pass (SAVED kernels)
   const float* grad_sums;
   float* partial_T;   // [num_ctas][2][12]
   float min_disp, disp_range;
@@ -42,53 +46,81 @@ constexpr int SM_COEF = SM_LID + 2 * CPLANE;
 constexpr int SM_GT = SM_COEF + 10 * CPLANE;
 constexpr int SM_TOTAL = SM_GT + 9 * GPLANE;
 
-struct WinStats {
-  float mu_x, sig_x, sig_xy;
+// Per-position SSIM statistics of all three channels and both frames from 3x3 windows, produced by a
+// register ring that marches down one column of the halo-2 tiles (3 horizontal taps per row from
+// shared memory).  `emit(k, st)` is called for output row k (0..R-1) of the run.
+struct PosStats {
+  float mu_y[3], sig_y[3];
+  float mu_x[2][3], sig_x[2][3], sig_xy[2][3];
+  float yc[3], xc[2][3];   // centre values (L1 term)
 };
 
-// 3x3 statistics around halo-2 tile position (centre row cr, centre col cc) for one channel plane
-__device__ __forceinline__ void window_y(const float* __restrict__ Yc, int cr, int cc, float& mu_y, float& sig_y) {
-  float s = 0.f, ss = 0.f;
+template <int F, int R, typename Emit>
+__device__ __forceinline__ void march_stats(const float* __restrict__ Y, const float* __restrict__ X, int row0, int col0,
+                                            Emit emit) {
+  const float inv9 = 1.f / 9.f;
+  float ay[3], by[3], ayy[3], byy[3];
+  float ax[2][3], bx[2][3], axx[2][3], bxx[2][3], axy[2][3], bxy[2][3];
 #pragma unroll
-  for (int dy = -1; dy <= 1; ++dy)
+  for (int ch = 0; ch < 3; ++ch) {
+    ay[ch] = by[ch] = ayy[ch] = byy[ch] = 0.f;
 #pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const float v = Yc[(cr + dy) * PITCH2 + cc + dx];
-      s += v;
-      ss += v * v;
+    for (int f = 0; f < 2; ++f) ax[f][ch] = bx[f][ch] = axx[f][ch] = bxx[f][ch] = axy[f][ch] = bxy[f][ch] = 0.f;
+  }
+#pragma unroll
+  for (int rr = 0; rr < R + 2; ++rr) {
+    const int o = (row0 + rr) * PITCH2 + col0;
+    PosStats st;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float* Yc = Y + ch * PLANE2 + o;
+      const float yl = Yc[0], ym = Yc[1], yr = Yc[2];
+      const float hy = yl + ym + yr, hyy = yl * yl + ym * ym + yr * yr;
+      if (rr >= 2) {
+        st.mu_y[ch] = (ay[ch] + hy) * inv9;
+        st.sig_y[ch] = (ayy[ch] + hyy) * inv9 - st.mu_y[ch] * st.mu_y[ch];
+        st.yc[ch] = Yc[1 - PITCH2];
+      }
+      ay[ch] = by[ch] + hy, by[ch] = hy, ayy[ch] = byy[ch] + hyy, byy[ch] = hyy;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const float* Xc = X + (f * 3 + ch) * PLANE2 + o;
+        const float xl = Xc[0], xm = Xc[1], xr = Xc[2];
+        const float hx = xl + xm + xr, hxx = xl * xl + xm * xm + xr * xr, hxy = xl * yl + xm * ym + xr * yr;
+        if (rr >= 2) {
+          const float mu = (ax[f][ch] + hx) * inv9;
+          st.mu_x[f][ch] = mu;
+          st.sig_x[f][ch] = (axx[f][ch] + hxx) * inv9 - mu * mu;
+          st.sig_xy[f][ch] = (axy[f][ch] + hxy) * inv9 - mu * st.mu_y[ch];
+          st.xc[f][ch] = Xc[1 - PITCH2];
+        }
+        ax[f][ch] = bx[f][ch] + hx, bx[f][ch] = hx;
+        axx[f][ch] = bxx[f][ch] + hxx, bxx[f][ch] = hxx;
+        axy[f][ch] = bxy[f][ch] + hxy, bxy[f][ch] = hxy;
+      }
     }
-  mu_y = s / 9.f;
-  sig_y = ss / 9.f - mu_y * mu_y;
+    if (rr >= 2) emit(rr - 2, st);
+  }
 }
 
-__device__ __forceinline__ WinStats window_x(const float* __restrict__ Xc, const float* __restrict__ Yc, int cr,
-                                             int cc, float mu_y) {
-  float s = 0.f, ss = 0.f, sxy = 0.f;
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int o = (cr + dy) * PITCH2 + cc + dx;
-      const float v = Xc[o];
-      s += v;
-      ss += v * v;
-      sxy += v * Yc[o];
-    }
-  WinStats w;
-  w.mu_x = s / 9.f;
-  w.sig_x = ss / 9.f - w.mu_x * w.mu_x;
-  w.sig_xy = sxy / 9.f - w.mu_x * mu_y;
-  return w;
-}
-
-__device__ __forceinline__ float ssim_value(const WinStats& w, float mu_y, float sig_y) {
+__device__ __forceinline__ float ssim_raw(float mu_x, float sig_x, float sig_xy, float mu_y, float sig_y) {
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-  const float n = (2.f * w.mu_x * mu_y + C1) * (2.f * w.sig_xy + C2);
-  const float dn = (w.mu_x * w.mu_x + mu_y * mu_y + C1) * (w.sig_x + sig_y + C2);
-  return (1.f - n / dn) / 2.f;
+  const float n = (2.f * mu_x * mu_y + C1) * (2.f * sig_xy + C2);
+  const float dn = (mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2);
+  return (1.f - n * __frcp_rn(dn)) * 0.5f;
 }
 
-template <int MODE, int F>
+// weight with which full-resolution sample `dst` reads low-resolution sample `i` under bilinear
+// up-sampling by 2^shift (align_corners=False): triangle kernel on the clamped source coordinate
+__device__ __forceinline__ float tri_weight(int dst, int shift, int n_in, int i) {
+  const float src = fminf(fmaxf(((float)dst + 0.5f) * (1.f / (float)(1 << shift)) - 0.5f, 0.f), (float)(n_in - 1));
+  return fmaxf(0.f, 1.f - fabsf(src - (float)i));
+}
+
+constexpr int B_RUN = 3;                       // rows per stage-B thread
+constexpr int B_THREADS = H1_W * (H1_H / B_RUN);   // 34 * 6 = 204
+
+template <int MODE, int F, bool SAVED>
 __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ CamConst cam;
@@ -134,25 +166,21 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
   __syncthreads();
 
   if (automask) {   // identity candidate losses on the 1-pixel halo (level independent)
-    for (int i = tid; i < H1_W * H1_H; i += WP_THREADS) {
-      const int pr = i / H1_W, pc = i - pr * H1_W;
-      float acc_s[2] = {0.f, 0.f}, acc_l[2] = {0.f, 0.f};
+    if (tid < B_THREADS) {
+      const int pc = tid % H1_W, pr0 = (tid / H1_W) * B_RUN;
+      march_stats<F, B_RUN>(Y, smem + SM_X, pr0, pc, [&](int k, const PosStats& st) {
+        float acc_s[2] = {0.f, 0.f}, acc_l[2] = {0.f, 0.f};
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float* Yc = Y + ch * PLANE2;
-        float mu_y, sig_y;
-        window_y(Yc, pr + 1, pc + 1, mu_y, sig_y);
-        const float yc = Yc[(pr + 1) * PITCH2 + pc + 1];
+        for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-          const float* Xc = smem + SM_X + (f * 3 + ch) * PLANE2;
-          const WinStats w = window_x(Xc, Yc, pr + 1, pc + 1, mu_y);
-          acc_s[f] += fminf(fmaxf(ssim_value(w, mu_y, sig_y), 0.f), 1.f);
-          acc_l[f] += fabsf(yc - Xc[(pr + 1) * PITCH2 + pc + 1]);
-        }
-      }
+          for (int f = 0; f < F; ++f) {
+            acc_s[f] += fminf(fmaxf(ssim_raw(st.mu_x[f][ch], st.sig_x[f][ch], st.sig_xy[f][ch], st.mu_y[ch], st.sig_y[ch]), 0.f), 1.f);
+            acc_l[f] += fabsf(st.yc[ch] - st.xc[f][ch]);
+          }
 #pragma unroll
-      for (int f = 0; f < F; ++f) LID[f * CPLANE + pr * CPITCH + pc] = ssim_w * (acc_s[f] / 3.f) + l1_w * (acc_l[f] / 3.f);
+        for (int f = 0; f < F; ++f)
+          LID[f * CPLANE + (pr0 + k) * CPITCH + pc] = ssim_w * (acc_s[f] * (1.f / 3.f)) + l1_w * (acc_l[f] * (1.f / 3.f));
+      });
     }
     __syncthreads();
   }
@@ -169,114 +197,131 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
     const size_t p_lo = (size_t)h * w;
     const float* disp = d.disp[si] + (size_t)b * p_lo;
     const float g_photo = __ldg(a.grad_sums + si * DD_NSUM + DD_SUM_PHOTO);
+    const float g_coef = (-0.5f * (ssim_w / 3.f) * g_photo) / 9.f;   // d loss / d S per window tap
 
-    // ---- stage A: warp both frames over the 2-pixel halo ----------------------------------------
-    for (int i = tid; i < H2_W * H2_H; i += WP_THREADS) {
-      const int hr = i / H2_W, hc = i - hr * H2_W;
-      const int ri = r0 - 2 + hr, ci = c0 - 2 + hc;
-      const bool used = ri >= -1 && ri <= H && ci >= -1 && ci <= W;
-      const int so = hr * PITCH2 + hc;
-      if (!used) {
+    // ---- stage A: warped frames over the 2-pixel halo --------------------------------------------
+    if (SAVED) {
+      for (int i = tid; i < H2_W * H2_H; i += WP_THREADS) {
+        const int hr = i / H2_W, hc = i - hr * H2_W;
+        const int ri = r0 - 2 + hr, ci = c0 - 2 + hc;
+        const bool used = ri >= -1 && ri <= H && ci >= -1 && ci <= W;
+        const size_t o = (size_t)reflect1(max(min(ri, H), -1), H) * W + reflect1(max(min(ci, W), -1), W);
+        const int so = hr * PITCH2 + hc;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) smem[SM_X + k * PLANE2 + so] = 0.f;
-        continue;
-      }
-      const int r = reflect1(ri, H), c = reflect1(ci, W);
-      const Taps ty = up_taps(r, shift, h), tx = up_taps(c, shift, w);
-      PixelGeom pg;
-      const float du = bilerp(disp, w, ty, tx);
-      pg.depth = 1.f / (a.min_disp + a.disp_range * du);
-      const float u = (float)c, v = (float)r;
-      pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
-                cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};
-      pg.Pc = {pg.depth * pg.ray.x, pg.depth * pg.ray.y, pg.depth * pg.ray.z};
+        for (int f = 0; f < F; ++f) {
+          const float* wsrc = a.warped_saved[si][f] + (size_t)b * 3 * P + o;
 #pragma unroll
-      for (int f = 0; f < F; ++f) {
-        Vec3 cf = {0.f, 0.f, 0.f};
-        float m = 1.f;
-        if (MODE >= 1) {
-          const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo;
-          const float tsv = cam.ts[f];
-          cf = {bilerp(fl, w, ty, tx) * tsv, bilerp(fl + p_lo, w, ty, tx) * tsv, bilerp(fl + 2 * p_lo, w, ty, tx) * tsv};
-          if (MODE == 2) m = bilerp(d.mask[si][f] + (size_t)b * p_lo, w, ty, tx);
+          for (int ch = 0; ch < 3; ++ch) smem[SM_X + (f * 3 + ch) * PLANE2 + so] = used ? __ldg(wsrc + ch * P) : 0.f;
         }
-        FrameGeom g;
-        frame_geometry<MODE>(g, pg, &cam, f, cf, m, H, W, false);
-        const Foot ft = footprint(unnormalise(g.gx, W), unnormalise(g.gy, H), H, W);
-        const float* src = d.source[f] + (size_t)b * 3 * P;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) smem[SM_X + (f * 3 + ch) * PLANE2 + so] = sample_plane(src + ch * P, W, ft);
       }
+      __syncthreads();
+    } else {
+      for (int i = tid; i < H2_W * H2_H; i += WP_THREADS) {
+        const int hr = i / H2_W, hc = i - hr * H2_W;
+        const int ri = r0 - 2 + hr, ci = c0 - 2 + hc;
+        const bool used = ri >= -1 && ri <= H && ci >= -1 && ci <= W;
+        const int so = hr * PITCH2 + hc;
+        if (!used) {
+  #pragma unroll
+          for (int k = 0; k < 6; ++k) smem[SM_X + k * PLANE2 + so] = 0.f;
+          continue;
+        }
+        const int r = reflect1(ri, H), c = reflect1(ci, W);
+        const Taps ty = up_taps(r, shift, h), tx = up_taps(c, shift, w);
+        PixelGeom pg;
+        const float du = bilerp(disp, w, ty, tx);
+        pg.depth = __frcp_rn(a.min_disp + a.disp_range * du);
+        const float u = (float)c, v = (float)r;
+        pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
+                  cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};
+        pg.Pc = {pg.depth * pg.ray.x, pg.depth * pg.ray.y, pg.depth * pg.ray.z};
+  #pragma unroll
+        for (int f = 0; f < F; ++f) {
+          Vec3 cf = {0.f, 0.f, 0.f};
+          float m = 1.f;
+          if (MODE >= 1) {
+            const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo;
+            const float tsv = cam.ts[f];
+            cf = {bilerp(fl, w, ty, tx) * tsv, bilerp(fl + p_lo, w, ty, tx) * tsv, bilerp(fl + 2 * p_lo, w, ty, tx) * tsv};
+            if (MODE == 2) m = bilerp(d.mask[si][f] + (size_t)b * p_lo, w, ty, tx);
+          }
+          FrameGeom g;
+          frame_geometry<MODE>(g, pg, &cam, f, cf, m, H, W, false);
+          const Foot ft = footprint(unnormalise(g.gx, W), unnormalise(g.gy, H), H, W);
+          const float* src = d.source[f] + (size_t)b * 3 * P;
+  #pragma unroll
+          for (int ch = 0; ch < 3; ++ch) smem[SM_X + (f * 3 + ch) * PLANE2 + so] = sample_plane(src + ch * P, W, ft);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
 
     // ---- stage B: statistics, selection and coefficient maps on the 1-pixel halo -----------------
-    for (int i = tid; i < H1_W * H1_H; i += WP_THREADS) {
-      const int pr = i / H1_W, pc = i - pr * H1_W;
-      const int ri = r0 - 1 + pr, ci = c0 - 1 + pc;
-      float* co = COEF + pr * CPITCH + pc;
-      if (ri < 0 || ri >= H || ci < 0 || ci >= W) {
-        co[0] = __int_as_float(-1);
-        continue;
-      }
-      WinStats ws[2][3];
-      float mu_y[3], sig_y[3];
-      float acc_s[2] = {0.f, 0.f}, acc_l[2] = {0.f, 0.f};
-      bool gate[2][3];
+    if (tid < B_THREADS) {
+      const int pc = tid % H1_W, pr0 = (tid / H1_W) * B_RUN;
+      const int ci = c0 - 1 + pc;
+      march_stats<F, B_RUN>(Y, smem + SM_X, pr0, pc, [&](int k, const PosStats& st) {
+        const int pr = pr0 + k;
+        const int ri = r0 - 1 + pr;
+        float* co = COEF + pr * CPITCH + pc;
+        if (ri < 0 || ri >= H || ci < 0 || ci >= W) {
+          co[0] = __int_as_float(-1);
+          return;
+        }
+        float vraw[2][3];
+        float acc_s[2] = {0.f, 0.f}, acc_l[2] = {0.f, 0.f};
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float* Yc = Y + ch * PLANE2;
-        window_y(Yc, pr + 1, pc + 1, mu_y[ch], sig_y[ch]);
-        const float yc = Yc[(pr + 1) * PITCH2 + pc + 1];
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            vraw[f][ch] = ssim_raw(st.mu_x[f][ch], st.sig_x[f][ch], st.sig_xy[f][ch], st.mu_y[ch], st.sig_y[ch]);
+            acc_s[f] += fminf(fmaxf(vraw[f][ch], 0.f), 1.f);
+            acc_l[f] += fabsf(st.yc[ch] - st.xc[f][ch]);
+          }
+        // per-pixel argmin over {identity(+noise), warped} with first-index tie-break (Trainer.py:339-347)
+        float best = 0.f;
+        int arg = -1;
+        bool first = true;
+        const size_t o = (size_t)ri * W + ci;
+        if (automask) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float v = LID[f * CPLANE + pr * CPITCH + pc];
+            if (d.noise[si]) v += __ldg(d.noise[si] + ((size_t)b * F + f) * P + o) * 0.00001f;
+            if (first || v < best) best = v, arg = -1, first = false;
+          }
+        }
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          const float* Xc = smem + SM_X + (f * 3 + ch) * PLANE2;
-          ws[f][ch] = window_x(Xc, Yc, pr + 1, pc + 1, mu_y[ch]);
-          const float v = ssim_value(ws[f][ch], mu_y[ch], sig_y[ch]);
-          gate[f][ch] = (v >= 0.f) && (v <= 1.f);   // torch.clamp passes the gradient on the closed interval
-          acc_s[f] += fminf(fmaxf(v, 0.f), 1.f);
-          acc_l[f] += fabsf(yc - Xc[(pr + 1) * PITCH2 + pc + 1]);
+          const float v = ssim_w * (acc_s[f] * (1.f / 3.f)) + l1_w * (acc_l[f] * (1.f / 3.f));
+          if (first || v < best) best = v, arg = f, first = false;
         }
-      }
-      // per-pixel argmin over {identity(+noise), warped} with first-index tie-break (Trainer.py:339-347)
-      float best = 0.f;
-      int arg = -1;
-      bool first = true;
-      const size_t o = (size_t)ri * W + ci;
-      if (automask) {
+        co[0] = __int_as_float(arg);
+        if (arg >= 0) {
+          const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+          const int fs = arg == 0 ? 0 : F - 1;
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-          float v = LID[f * CPLANE + pr * CPITCH + pc];
-          if (d.noise[si]) v += __ldg(d.noise[si] + ((size_t)b * F + f) * P + o) * 0.00001f;
-          if (first || v < best) best = v, arg = -1, first = false;
+          for (int ch = 0; ch < 3; ++ch) {
+            const float mx = fs == 0 ? st.mu_x[0][ch] : st.mu_x[F - 1][ch];
+            const float sx = fs == 0 ? st.sig_x[0][ch] : st.sig_x[F - 1][ch];
+            const float sxy = fs == 0 ? st.sig_xy[0][ch] : st.sig_xy[F - 1][ch];
+            const float vr = fs == 0 ? vraw[0][ch] : vraw[F - 1][ch];
+            const bool gt = (vr >= 0.f) && (vr <= 1.f);   // torch.clamp passes the gradient on the closed interval
+            const float my = st.mu_y[ch], sy = st.sig_y[ch];
+            const float A1 = 2.f * mx * my + C1, A2 = 2.f * sxy + C2;
+            const float B1 = mx * mx + my * my + C1, B2 = sx + sy + C2;
+            const float n = A1 * A2, dn = B1 * B2;
+            const float inv_d = __frcp_rn(dn);
+            const float dS_dmu = (2.f * my * (A2 - A1) * dn - n * 2.f * mx * (B2 - B1)) * inv_d * inv_d;
+            const float dS_dxx = -n * B1 * inv_d * inv_d;
+            const float dS_dxy = 2.f * A1 * inv_d;
+            const float G = gt ? g_coef : 0.f;
+            co[(1 + ch * 3 + 0) * CPLANE] = G * dS_dmu;
+            co[(1 + ch * 3 + 1) * CPLANE] = G * 2.f * dS_dxx;
+            co[(1 + ch * 3 + 2) * CPLANE] = G * dS_dxy;
+          }
         }
-      }
-#pragma unroll
-      for (int f = 0; f < F; ++f) {
-        const float v = ssim_w * (acc_s[f] / 3.f) + l1_w * (acc_l[f] / 3.f);
-        if (first || v < best) best = v, arg = f, first = false;
-      }
-      co[0] = __int_as_float(arg);
-      if (arg >= 0) {
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          const WinStats s = arg == 0 ? ws[0][ch] : ws[F - 1][ch];
-          const bool gt = arg == 0 ? gate[0][ch] : gate[F - 1][ch];
-          const float my = mu_y[ch], sy = sig_y[ch];
-          const float A1 = 2.f * s.mu_x * my + C1, A2 = 2.f * s.sig_xy + C2;
-          const float B1 = s.mu_x * s.mu_x + my * my + C1, B2 = s.sig_x + sy + C2;
-          const float n = A1 * A2, dn = B1 * B2;
-          const float inv_d = 1.f / dn;
-          const float dS_dmu = (2.f * my * (A2 - A1) * dn - n * 2.f * s.mu_x * (B2 - B1)) * inv_d * inv_d;
-          const float dS_dxx = -n * B1 * inv_d * inv_d;
-          const float dS_dxy = 2.f * A1 * inv_d;
-          const float G = gt ? (-0.5f * (ssim_w / 3.f) * g_photo) / 9.f : 0.f;
-          co[(1 + ch * 3 + 0) * CPLANE] = G * dS_dmu;
-          co[(1 + ch * 3 + 1) * CPLANE] = G * 2.f * dS_dxx;
-          co[(1 + ch * 3 + 2) * CPLANE] = G * dS_dxy;
-        }
-      }
+      });
     }
     __syncthreads();
 
@@ -286,33 +331,43 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
     for (int k = 0; k < 2; ++k) {
       const int qr = warp * 2 + k, qc = lane;      // tile coordinates
       const int r = r0 + qr, c = c0 + qc;
-      // weights of the 3x3 neighbourhood of windows (reflect fold-back)
-      float gcol[2][3];
+      // box-sum of the coefficient maps over the 3x3 neighbourhood of windows (reflect fold-back weights);
+      // grad x_f(q) = A_f + x_f(q) * B_f + y(q) * C_f per channel
+      float cA[2][3], cB[2][3], cC[2][3];
 #pragma unroll
-      for (int f = 0; f < 2; ++f) gcol[f][0] = gcol[f][1] = gcol[f][2] = 0.f;
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) cA[f][ch] = cB[f][ch] = cC[f][ch] = 0.f;
       bool any[2] = {false, false};
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy) {
         const int prr = r + dy;
-        if (prr < 0 || prr >= H) continue;
         const float wr = ((r == 1 && prr == 0) || (r == H - 2 && prr == H - 1)) ? 2.f : 1.f;
 #pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
           const int pcc = c + dx;
-          if (pcc < 0 || pcc >= W) continue;
-          const float wc = ((c == 1 && pcc == 0) || (c == W - 2 && pcc == W - 1)) ? 2.f : 1.f;
           const float* co = COEF + (qr + 1 + dy) * CPITCH + (qc + 1 + dx);
-          const int sel = __float_as_int(co[0]);
+          const int sel = __float_as_int(co[0]);   // -1 outside the image or when an identity candidate won
           if (sel < 0) continue;
-          const float wgt = wr * wc;
-          const float yq0 = Y[0 * PLANE2 + (qr + 2) * PITCH2 + qc + 2], yq1 = Y[1 * PLANE2 + (qr + 2) * PITCH2 + qc + 2],
-                      yq2 = Y[2 * PLANE2 + (qr + 2) * PITCH2 + qc + 2];
-          const float* Xq = smem + SM_X + sel * 3 * PLANE2 + (qr + 2) * PITCH2 + qc + 2;
-          const float g0 = wgt * (co[1 * CPLANE] + Xq[0] * co[2 * CPLANE] + yq0 * co[3 * CPLANE]);
-          const float g1 = wgt * (co[4 * CPLANE] + Xq[PLANE2] * co[5 * CPLANE] + yq1 * co[6 * CPLANE]);
-          const float g2 = wgt * (co[7 * CPLANE] + Xq[2 * PLANE2] * co[8 * CPLANE] + yq2 * co[9 * CPLANE]);
-          if (sel == 0) gcol[0][0] += g0, gcol[0][1] += g1, gcol[0][2] += g2, any[0] = true;
-          else gcol[1][0] += g0, gcol[1][1] += g1, gcol[1][2] += g2, any[1] = true;
+          const float wgt = wr * (((c == 1 && pcc == 0) || (c == W - 2 && pcc == W - 1)) ? 2.f : 1.f);
+          const int fs = sel == 0 ? 0 : 1;
+          any[fs] = true;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const float va = wgt * co[(1 + ch * 3) * CPLANE], vb = wgt * co[(2 + ch * 3) * CPLANE], vc = wgt * co[(3 + ch * 3) * CPLANE];
+            if (fs == 0) cA[0][ch] += va, cB[0][ch] += vb, cC[0][ch] += vc;
+            else cA[1][ch] += va, cB[1][ch] += vb, cC[1][ch] += vc;
+          }
+        }
+      }
+      float gcol[2][3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float yq = Y[ch * PLANE2 + (qr + 2) * PITCH2 + qc + 2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float xq = smem[SM_X + (f * 3 + ch) * PLANE2 + (qr + 2) * PITCH2 + qc + 2];
+          gcol[f][ch] = cA[f][ch] + xq * cB[f][ch] + yq * cC[f][ch];
         }
       }
       {   // L1 term of the centre pixel (Trainer.py:417-418)
@@ -356,7 +411,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
       PixelGeom pg;
       {
         const float du = bilerp(disp, w, ty, tx);
-        pg.depth = 1.f / (a.min_disp + a.disp_range * du);
+        pg.depth = __frcp_rn(a.min_disp + a.disp_range * du);
         const float u = (float)c, v = (float)r;
         pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
                   cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};
@@ -393,7 +448,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
             giy += gcol[f][ch] * ((sw - nw) * ft.wx0 + (se - ne) * ft.wx1);
           }
           const float gpx = ft.live_x ? gix : 0.f, gpy = ft.live_y ? giy : 0.f;   // GridSampler.cuh:64-80
-          const float iz = 1.f / g.pr.z;
+          const float iz = g.pr.iz;
           const float gc0 = gpx * iz, gc1 = gpy * iz, gc2 = -(gpx * g.pr.px + gpy * g.pr.py) * iz;
           const float* K = cam.K;
           const Vec3 gX = {K[0] * gc0 + K[4] * gc1 + K[8] * gc2, K[1] * gc0 + K[5] * gc1 + K[9] * gc2,
@@ -479,51 +534,57 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
     }
     __syncthreads();
 
-    // ---- stage D: transposed bilinear up-sampling (levels > 0) ------------------------------------
+    // ---- stage D: transposed bilinear up-sampling (levels > 0), rows then columns ---------------------
     if (shift != 0) {
       const int tl_h = (BT_H >> shift) + 2, tl_w = (BT_W >> shift) + 2;
-      const int n_lo = tl_h * tl_w;
       const int narr = MODE == 0 ? 1 : (MODE == 1 ? 7 : 9);
-      const int win = 2 << shift;                     // taps per axis that can reach one low-res sample
-      const int G = min(32, 1 << (2 * shift));        // lanes cooperating on one (array, low-res pixel)
-      const int per_pass = WP_THREADS / G;
-      const int sub = tid % G, slot = tid / G;
-      const int ntask = narr * n_lo;
-      for (int t0 = 0; t0 < ntask; t0 += per_pass) {
-        const int t = t0 + slot;
+      const int win = 2 << shift, half = 1 << (shift - 1);
+      float* V = COEF;   // [narr][tl_h][32] -- the coefficient maps are dead after stage C
+      // pass 1: V[a][li][c] = sum over the tile rows that read low-res row gi of wy * GT[a][row][c]
+      for (int t = tid; t < narr * tl_h * BT_W; t += WP_THREADS) {
+        const int cx = t & (BT_W - 1);
+        const int al = t >> 5;
+        const int arr = al / tl_h, li = al - arr * tl_h;
+        const int gi = (r0 >> shift) - 1 + li;
         float acc = 0.f;
-        int arr = 0, gi = 0, gj = 0;
-        bool ok = false;
-        if (t < ntask) {
-          arr = t / n_lo;
-          const int lp = t - arr * n_lo;
-          const int li = lp / tl_w, lj = lp - li * tl_w;
-          gi = (r0 >> shift) - 1 + li, gj = (c0 >> shift) - 1 + lj;
-          ok = gi >= 0 && gi < h && gj >= 0 && gj < w;
-          if (ok) {
-            const int rs = (gi << shift) - (1 << (shift - 1)), cs = (gj << shift) - (1 << (shift - 1));
-            for (int e = sub; e < win * win; e += G) {
-              const int rr = rs + e / win, cc = cs + e % win;
-              if (rr < r0 || rr >= r0 + BT_H || cc < c0 || cc >= c0 + BT_W) continue;
-              const float wgt = up_weight(rr, shift, h, gi) * up_weight(cc, shift, w, gj);
-              acc += wgt * GT[arr * GPLANE + (rr - r0) * BT_W + (cc - c0)];
-            }
+        if (gi >= 0 && gi < h) {
+          const int rs = (gi << shift) - half;
+          for (int e = 0; e < win; ++e) {
+            const int rr = rs + e;
+            if (rr < r0 || rr >= r0 + BT_H) continue;
+            acc += tri_weight(rr, shift, h, gi) * GT[arr * GPLANE + (rr - r0) * BT_W + cx];
           }
         }
-        for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (ok && sub == 0 && acc != 0.f) {
-          const size_t ol = (size_t)gi * w + gj;
-          float* dst = nullptr;
-          if (arr == 0) dst = want_disp ? a.g.disp[si] + (size_t)b * p_lo + ol : nullptr;
-          else if (arr < 7) {
-            const int f = (arr - 1) / 3, ch = (arr - 1) % 3;
-            dst = (f < F && a.g.flow[si][f]) ? a.g.flow[si][f] + ((size_t)b * 3 + ch) * p_lo + ol : nullptr;
-          } else {
-            const int f = arr - 7;
-            dst = (f < F && a.g.mask[si][f]) ? a.g.mask[si][f] + (size_t)b * p_lo + ol : nullptr;
-          }
-          if (dst) atomicAdd(dst, acc);
+        V[t] = acc;
+      }
+      __syncthreads();
+      // pass 2: out[a][li][lj] = sum over the tile columns that read low-res column gj of wx * V[a][li][col]
+      for (int t = tid; t < narr * tl_h * tl_w; t += WP_THREADS) {
+        const int lj = t % tl_w;
+        const int al = t / tl_w;
+        const int arr = al / tl_h, li = al - arr * tl_h;
+        const int gi = (r0 >> shift) - 1 + li, gj = (c0 >> shift) - 1 + lj;
+        if (gi < 0 || gi >= h || gj < 0 || gj >= w) continue;
+        const int cs = (gj << shift) - half;
+        float acc = 0.f;
+        for (int e = 0; e < win; ++e) {
+          const int cc = cs + e;
+          if (cc < c0 || cc >= c0 + BT_W) continue;
+          acc += tri_weight(cc, shift, w, gj) * V[al * BT_W + (cc - c0)];
         }
+        if (acc == 0.f) continue;
+        const size_t ol = (size_t)gi * w + gj;
+        float* dst = nullptr;
+        if (arr == 0) {
+          dst = want_disp ? a.g.disp[si] + (size_t)b * p_lo + ol : nullptr;
+        } else if (arr < 7) {
+          const int f = (arr - 1) / 3, ch = (arr - 1) - f * 3;
+          dst = (f < F && a.g.flow[si][f]) ? a.g.flow[si][f] + ((size_t)b * 3 + ch) * p_lo + ol : nullptr;
+        } else {
+          const int f = arr - 7;
+          dst = (f < F && a.g.mask[si][f]) ? a.g.mask[si][f] + (size_t)b * p_lo + ol : nullptr;
+        }
+        if (dst) atomicAdd(dst, acc);
       }
       __syncthreads();
     }
@@ -563,9 +624,9 @@ __global__ void finalize_T_kernel(const float* __restrict__ partial, float* __re
 
 int validate_desc(const dd_warp_desc* d);
 
-template <int MODE, int F>
+template <int MODE, int F, bool SAVED>
 static int launch_bwd(const BwdArgs& args, dim3 grid, cudaStream_t st) {
-  auto kern = warp_photo_bwd_kernel<MODE, F>;
+  auto kern = warp_photo_bwd_kernel<MODE, F, SAVED>;
   const size_t smem_bytes = SM_TOTAL * sizeof(float);
   DD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   kern<<<grid, WP_THREADS, smem_bytes, st>>>(args); dd::count_launches(1);
@@ -613,12 +674,21 @@ int warp_photo_bwd_impl(const dd_warp_desc* desc, const float* grad_sums, const 
   }
   const dim3 grid(desc->W / BT_W, desc->H / BT_H, desc->B);
   const int F = desc->num_frames;
-  if (mode == 0 && F == 2) rc = launch_bwd<0, 2>(args, grid, st);
-  else if (mode == 1 && F == 2) rc = launch_bwd<1, 2>(args, grid, st);
-  else if (mode == 2 && F == 2) rc = launch_bwd<2, 2>(args, grid, st);
-  else if (mode == 0 && F == 1) rc = launch_bwd<0, 1>(args, grid, st);
-  else if (mode == 1 && F == 1) rc = launch_bwd<1, 1>(args, grid, st);
-  else rc = launch_bwd<2, 1>(args, grid, st);
+  bool have_warped = saved != nullptr;
+  for (int s = 0; s < desc->num_scales && have_warped; ++s)
+    for (int f = 0; f < F; ++f) {
+      if (!saved->warped[s][f]) have_warped = false;
+      else args.warped_saved[s][f] = saved->warped[s][f];
+    }
+#define DD_BWD(M, FF)                                                      \
+  rc = have_warped ? launch_bwd<M, FF, true>(args, grid, st) : launch_bwd<M, FF, false>(args, grid, st)
+  if (mode == 0 && F == 2) DD_BWD(0, 2);
+  else if (mode == 1 && F == 2) DD_BWD(1, 2);
+  else if (mode == 2 && F == 2) DD_BWD(2, 2);
+  else if (mode == 0 && F == 1) DD_BWD(0, 1);
+  else if (mode == 1 && F == 1) DD_BWD(1, 1);
+  else DD_BWD(2, 1);
+#undef DD_BWD
   if (rc != DD_OK) return rc;
   if (grads->T[0] || grads->T[1]) {
     finalize_T_kernel<<<desc->B, 32, 0, st>>>(args.partial_T, grads->T[0], F > 1 ? grads->T[1] : nullptr,

@@ -44,6 +44,7 @@ __device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const f
                                             const float* __restrict__ X1, int lane, int row0, float ssim_w,
                                             float l1_w, SsimOut& out) {
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  const float inv9 = 1.f / 9.f, inv3 = 1.f / 3.f;   // window / channel means as multiplies (<= 1 ulp from the divisions)
   float ssim_acc[2][4], l1_acc[2][4];
 #pragma unroll
   for (int f = 0; f < 2; ++f)
@@ -75,17 +76,17 @@ __device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const f
       }
       if (rr >= 2) {
         const int k = rr - 2;   // output row row0+k, centre halo row row0+k+1 == previous iteration
-        const float mu_y = (ay + hy) / 9.f;
-        const float e_yy = (ayy + hyy) / 9.f;
+        const float mu_y = (ay + hy) * inv9;
+        const float e_yy = (ayy + hyy) * inv9;
         const float sig_y = e_yy - mu_y * mu_y;
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          const float mu_x = (ax[f] + hx[f]) / 9.f;
-          const float sig_x = (axx[f] + hxx[f]) / 9.f - mu_x * mu_x;
-          const float sig_xy = (axy[f] + hxy[f]) / 9.f - mu_x * mu_y;
+          const float mu_x = (ax[f] + hx[f]) * inv9;
+          const float sig_x = (axx[f] + hxx[f]) * inv9 - mu_x * mu_x;
+          const float sig_xy = (axy[f] + hxy[f]) * inv9 - mu_x * mu_y;
           const float n = (2.f * mu_x * mu_y + C1) * (2.f * sig_xy + C2);
           const float dn = (mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2);
-          const float s = fminf(fmaxf((1.f - n / dn) / 2.f, 0.f), 1.f);
+          const float s = fminf(fmaxf((1.f - n * __frcp_rn(dn)) * 0.5f, 0.f), 1.f);
           ssim_acc[f][k] += s;
           l1_acc[f][k] += fabsf(yc_prev - xc_prev[f]);
         }
@@ -104,7 +105,7 @@ __device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const f
 #pragma unroll
   for (int f = 0; f < F; ++f)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) out.L[f][k] = ssim_w * (ssim_acc[f][k] / 3.f) + l1_w * (l1_acc[f][k] / 3.f);
+    for (int k = 0; k < 4; ++k) out.L[f][k] = ssim_w * (ssim_acc[f][k] * inv3) + l1_w * (l1_acc[f][k] * inv3);
 }
 
 template <int MODE, int F>
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_fwd_kernel(const __g
       PixelGeom pg;
       {
         const float du = bilerp(disp, w, ty, tx);                      // Trainer.py:225
-        pg.depth = 1.f / (a.min_disp + a.disp_range * du);               // tools.py:291-298
+        pg.depth = __frcp_rn(a.min_disp + a.disp_range * du);            // tools.py:291-298
         const float u = (float)c, v = (float)r;
         pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
                   cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};            // tools.py:193

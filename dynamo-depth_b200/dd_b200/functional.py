@@ -26,6 +26,7 @@ class WarpConfig:
     mask_disp_thrd: float = 0.03
     # names of by-products to materialise: 'warped', 'sample', 'depth', 'ident_sel', 'resid', 'independ', 'mag'
     materialise: tuple = ()
+    keep_warped: bool = True   # keep ('color', f, s) for the backward pass (24 B per pixel and level) instead of re-warping
     aux: Dict = field(default_factory=dict)  # filled by the forward pass: (name, frame_index, level) -> tensor
 
     @property
@@ -126,6 +127,8 @@ class _ViewSynthesisFn(torch.autograd.Function):
         want = set(cfg.materialise)
         if cfg.motmask:
             want |= {"resid", "mag"}   # resid: needed by backward (levels > 0); mag: m_sparsity
+        if cfg.keep_warped and any(ctx.needs_input_grad):
+            want |= {"warped"}         # backward re-reads the warped frames instead of re-warping them
         aux = L.WarpAux()
         out = {}
         for i, s in enumerate(cfg.scales):
@@ -163,7 +166,7 @@ class _ViewSynthesisFn(torch.autograd.Function):
 
         ctx.cfg, ctx.nF = cfg, nF
         ctx.save_for_backward(*tensors)
-        ctx.saved_resid = {k: v for k, v in out.items() if k[0] == "resid"}
+        ctx.saved_aux = {k: v for k, v in out.items() if k[0] in ("resid", "warped")}
         return sums
 
     @staticmethod
@@ -223,8 +226,11 @@ class _ViewSynthesisFn(torch.autograd.Function):
                     pos += 1
 
         saved = L.WarpAux()
-        for (name, f, i), t in ctx.saved_resid.items():
-            saved.resid[i][f] = t.data_ptr()
+        for (name, f, i), t in ctx.saved_aux.items():
+            if name == "resid":
+                saved.resid[i][f] = t.data_ptr()
+            else:
+                saved.warped[i][f] = t.data_ptr()
         gs = grad_sums.contiguous().float()
         ws_bytes = lib.dd_warp_photo_workspace_bytes(C.byref(desc))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

@@ -23,8 +23,13 @@ def robust_report(got, ref, rtol=1e-4):
 
 
 def assert_close_robust(got, ref, rtol=1e-4, max_outlier_frac=2e-3, max_rel_l2=2e-2, what=""):
+    """A single argmin / floor flip perturbs a 3x3 full-resolution patch, i.e. up to ~16 samples of a
+    coarse pyramid level after the bilinear transpose; small maps therefore get an absolute allowance of
+    32 samples (two flips) on top of the relative one (0 stays 0: used for integrated quantities)."""
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     r = robust_report(got, ref, rtol)
+    if max_outlier_frac > 0:
+        max_outlier_frac = max(max_outlier_frac, 32.0 / ref.numel())
     assert r["outlier_frac"] <= max_outlier_frac, (what, r)
     assert r["rel_l2"] <= max_rel_l2, (what, r)
     return r

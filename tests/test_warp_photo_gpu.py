@@ -24,7 +24,7 @@ def oracle_photo(case, dtype=torch.float32):
     return cfg, outputs, leaves, losses
 
 
-def cuda_photo(case, cfg, materialise=()):
+def cuda_photo(case, cfg, materialise=(), keep_warped=True):
     from dd_b200 import functional as Fn
     from dd_b200 import _lib as L
 
@@ -33,7 +33,7 @@ def cuda_photo(case, cfg, materialise=()):
     outputs, leaves = case.fresh_outputs(torch.float32, dev)
     frames = [-1, 1]
     wc = Fn.WarpConfig(scales=case.scales, cmpflow=cfg.bool_CmpFlow, motmask=cfg.bool_MotMask, automask=cfg.automask,
-                       materialise=tuple(materialise))
+                       materialise=tuple(materialise), keep_warped=keep_warped)
     disps = [outputs[("disp", 0, s)] for s in case.scales]
     flows = [[outputs[("complete_flow", f, s)] for f in frames] for s in case.scales] if cfg.bool_CmpFlow else None
     masks = [[outputs[("motion_mask", f, s)] for f in frames] for s in case.scales] if cfg.bool_MotMask else None
@@ -59,11 +59,12 @@ def cuda_photo(case, cfg, materialise=()):
     return wc, leaves, terms, loss, sums
 
 
+@pytest.mark.parametrize("keep_warped", [True, False], ids=["saved_warp", "recompute"])
 @pytest.mark.parametrize("name", LOSS_CASE_NAMES)
-def test_photo_loss_and_grads_vs_oracle(name):
+def test_photo_loss_and_grads_vs_oracle(name, keep_warped):
     case = LossCase(name)
     cfg, o_out, o_leaves, o_losses = oracle_photo(case)
-    wc, leaves, terms, loss, sums = cuda_photo(case, cfg)
+    wc, leaves, terms, loss, sums = cuda_photo(case, cfg, keep_warped=keep_warped)
     torch.cuda.synchronize()
     assert float(loss) == pytest.approx(float(o_losses["loss"]), rel=1e-4)
     assert float(terms["p_photo"]) == pytest.approx(float(o_losses["loss_term/p_photo"]), rel=1e-4)
