@@ -58,6 +58,8 @@ struct ConvArgs {
   const float* residual;
   int act;
   float* out;
+  float* out1;      // channels >= split go to out1 (data gradient written straight into grad_x0 / grad_x1)
+  int split;        // 0 = single output tensor
   int tiles_x;
 };
 
@@ -163,7 +165,13 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_core_kernel(const __grid_co
     const int co = co0 + cg * CPT + c;
     if (co >= a.Cout) continue;
     const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
-    const size_t o = (((size_t)b * a.Cout + co) * a.Ho + y) * a.Wo + xb;
+    float* outp = a.out;
+    size_t o = (((size_t)b * a.Cout + co) * a.Ho + y) * a.Wo + xb;
+    if (a.split > 0) {   // two destination tensors with split / Cout-split channels
+      if (co < a.split) o = (((size_t)b * a.split + co) * a.Ho + y) * a.Wo + xb;
+      else outp = a.out1, o = (((size_t)b * (a.Cout - a.split) + (co - a.split)) * a.Ho + y) * a.Wo + xb;
+      if (outp == nullptr) continue;
+    }
     float v[8];
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -171,12 +179,12 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_core_kernel(const __grid_co
       if (a.residual && xb + p < a.Wo) v[p] += __ldg(a.residual + o + p);
     }
     if (xb + 7 < a.Wo && (a.Wo & 3) == 0) {
-      reinterpret_cast<float4*>(a.out + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
-      reinterpret_cast<float4*>(a.out + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      reinterpret_cast<float4*>(outp + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(outp + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
 #pragma unroll
       for (int p = 0; p < 8; ++p)
-        if (xb + p < a.Wo) a.out[o + p] = v[p];
+        if (xb + p < a.Wo) outp[o + p] = v[p];
     }
   }
 }
@@ -281,7 +289,6 @@ __global__ void conv_route_kernel(const __grid_constant__ RouteArgs a) {
 }
 
 // ---- weight gradient -------------------------------------------------------------------------
-constexpr int WG_CO = 32;            // output channels per CTA
 constexpr int WG_GPITCH = CT_H * CT_W + 4;   // 132
 
 struct WgradArgs {
@@ -293,37 +300,53 @@ struct WgradArgs {
   float* gw;         // (Cout, Cin, k, k), zero-initialised, accumulated with atomics
 };
 
-template <int KS>
+// Thread = (group of WCO output channels, one input channel): WCO*k*k accumulators, reduced over the
+// (image, tile) items of this z-slice; CTA = 16 channel groups x 8 input channels.
+template <int KS, int WCO>
 __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
   constexpr int KK = KS * KS;
   constexpr int HALO = KS / 2;
   constexpr int ROWS = CT_H + 2 * HALO, COLS = CT_W + 2 * HALO;
-  __shared__ __align__(16) float g_s[WG_CO * WG_GPITCH];
+  constexpr int CO_T = 16 * WCO;
+  __shared__ __align__(16) float g_s[CO_T * WG_GPITCH];
   __shared__ __align__(16) float v_s[CI_T * IN_PLANE];
 
   const int tid = threadIdx.x;
-  const int ci = tid & 7, cp = tid >> 3;   // thread owns output channels co0+2cp, co0+2cp+1 and input channel ci0+ci
-  const int co0 = blockIdx.x * WG_CO, ci0 = blockIdx.y * CI_T;
+  const int ci = tid & 7, cq = tid >> 3;   // output channels co0 + cq*WCO .. +WCO-1, input channel ci0 + ci
+  const int co0 = blockIdx.x * CO_T, ci0 = blockIdx.y * CI_T;
   const int n_tiles = a.tiles_x * a.tiles_y;
   const int n_items = a.B * n_tiles;
   const int it0 = blockIdx.z * a.items_per_split;
   const int it1 = min(n_items, it0 + a.items_per_split);
+  const bool vec_ok = (a.W & 3) == 0;
 
-  float acc[2][KK];
+  float acc[WCO][KK];
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
+  for (int c = 0; c < WCO; ++c)
 #pragma unroll
     for (int t = 0; t < KK; ++t) acc[c][t] = 0.f;
 
   for (int it = it0; it < it1; ++it) {
     const int b = it / n_tiles, tile = it - b * n_tiles;
     const int ty0 = (tile / a.tiles_x) * CT_H, tx0 = (tile % a.tiles_x) * CT_W;
-    for (int i = tid; i < WG_CO * CT_H * CT_W; i += CONV_THREADS) {
-      const int c = i / (CT_H * CT_W), px = i - c * (CT_H * CT_W);
-      const int y = ty0 + px / CT_W, x = tx0 + (px % CT_W);
-      float v = 0.f;
-      if (co0 + c < a.Cout && y < a.H && x < a.W) v = __ldg(a.g + (((size_t)b * a.Cout + co0 + c) * a.H + y) * a.W + x);
-      g_s[c * WG_GPITCH + px] = v;
+    // gradient tile: CO_T channels x 8 rows x 16 pixels, one float4 (4 pixels) per thread and step
+    for (int i = tid; i < CO_T * CT_H * (CT_W / 4); i += CONV_THREADS) {
+      const int c = i >> 5, rem = i & 31;
+      const int r = rem >> 2, q = rem & 3;
+      const int y = ty0 + r, x = tx0 + 4 * q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co0 + c < a.Cout && y < a.H) {
+        const float* src = a.g + (((size_t)b * a.Cout + co0 + c) * a.H + y) * a.W + x;
+        if (vec_ok && x + 3 < a.W) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          if (x < a.W) v.x = __ldg(src);
+          if (x + 1 < a.W) v.y = __ldg(src + 1);
+          if (x + 2 < a.W) v.z = __ldg(src + 2);
+          if (x + 3 < a.W) v.w = __ldg(src + 3);
+        }
+      }
+      *reinterpret_cast<float4*>(g_s + c * WG_GPITCH + r * CT_W + 4 * q) = v;
     }
     for (int i = tid; i < CI_T * ROWS * COLS; i += CONV_THREADS) {
       const int c = i / (ROWS * COLS);
@@ -338,9 +361,12 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
     for (int r = 0; r < CT_H; ++r) {
 #pragma unroll
       for (int xq = 0; xq < CT_W; xq += 4) {
-        const float4 ga = *reinterpret_cast<const float4*>(g_s + (2 * cp) * WG_GPITCH + r * CT_W + xq);
-        const float4 gb = *reinterpret_cast<const float4*>(g_s + (2 * cp + 1) * WG_GPITCH + r * CT_W + xq);
-        const float g0[4] = {ga.x, ga.y, ga.z, ga.w}, g1[4] = {gb.x, gb.y, gb.z, gb.w};
+        float gv[WCO][4];
+#pragma unroll
+        for (int c = 0; c < WCO; ++c) {
+          const float4 g4 = *reinterpret_cast<const float4*>(g_s + (cq * WCO + c) * WG_GPITCH + r * CT_W + xq);
+          gv[c][0] = g4.x, gv[c][1] = g4.y, gv[c][2] = g4.z, gv[c][3] = g4.w;
+        }
 #pragma unroll
         for (int dy = 0; dy < KS; ++dy) {
           const float* vp = v_s + ci * IN_PLANE + (r + dy) * IN_PITCH + xq;
@@ -354,10 +380,9 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
 #pragma unroll
           for (int dx = 0; dx < KS; ++dx)
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              acc[0][dy * KS + dx] = fmaf(g0[p], vr[p + dx], acc[0][dy * KS + dx]);
-              acc[1][dy * KS + dx] = fmaf(g1[p], vr[p + dx], acc[1][dy * KS + dx]);
-            }
+            for (int c = 0; c < WCO; ++c)
+#pragma unroll
+              for (int p = 0; p < 4; ++p) acc[c][dy * KS + dx] = fmaf(gv[c][p], vr[p + dx], acc[c][dy * KS + dx]);
         }
       }
     }
@@ -365,8 +390,8 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   }
   if (ci0 + ci < a.Cin) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int co = co0 + 2 * cp + c;
+    for (int c = 0; c < WCO; ++c) {
+      const int co = co0 + cq * WCO + c;
       if (co >= a.Cout) continue;
 #pragma unroll
       for (int t = 0; t < KK; ++t) atomicAdd(a.gw + ((size_t)co * a.Cin + ci0 + ci) * KK + t, acc[c][t]);
@@ -398,7 +423,7 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __rest
 
 // ---- host side ---------------------------------------------------------------------------------
 
-static inline int cpt_for(int cout) { return cout >= 48 ? 8 : (cout >= 24 ? 4 : (cout >= 12 ? 2 : 1)); }
+static inline int cpt_for(int cout) { return cout > 32 ? 8 : (cout > 16 ? 4 : (cout > 8 ? 2 : 1)); }
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -528,14 +553,22 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     wa.g = g, wa.B = d->B, wa.H = d->H, wa.W = d->W, wa.Cin = Cin, wa.Cout = d->Cout, wa.gw = grad_weight;
     wa.tiles_x = (d->W + CT_W - 1) / CT_W, wa.tiles_y = (d->H + CT_H - 1) / CT_H;
     const int n_items = d->B * wa.tiles_x * wa.tiles_y;
-    const int gx = (d->Cout + WG_CO - 1) / WG_CO, gy = (Cin + CI_T - 1) / CI_T;
-    int splits = (148 * 8 + gx * gy - 1) / (gx * gy);   // ~8 CTAs per SM in flight
+    const int wco = d->Cout > 32 ? 4 : (d->Cout > 16 ? 2 : 1);
+    const int gx = (d->Cout + 16 * wco - 1) / (16 * wco), gy = (Cin + CI_T - 1) / CI_T;
+    int splits = (148 * 6 + gx * gy - 1) / (gx * gy);   // ~6 CTAs per SM in flight
     splits = splits < 1 ? 1 : (splits > n_items ? n_items : splits);
     wa.items_per_split = (n_items + splits - 1) / splits;
     splits = (n_items + wa.items_per_split - 1) / wa.items_per_split;
     dim3 grid(gx, gy, splits);
-    if (d->ksize == 3) { conv_wgrad_kernel<3><<<grid, CONV_THREADS, 0, st>>>(wa); dd::count_launches(1); }
-    else { conv_wgrad_kernel<1><<<grid, CONV_THREADS, 0, st>>>(wa); dd::count_launches(1); }
+#define DD_WGRAD(KSZ)                                                                    \
+  do {                                                                                   \
+    if (wco == 4) conv_wgrad_kernel<KSZ, 4><<<grid, CONV_THREADS, 0, st>>>(wa);          \
+    else if (wco == 2) conv_wgrad_kernel<KSZ, 2><<<grid, CONV_THREADS, 0, st>>>(wa);     \
+    else conv_wgrad_kernel<KSZ, 1><<<grid, CONV_THREADS, 0, st>>>(wa);                   \
+    dd::count_launches(1);                                                               \
+  } while (0)
+    if (d->ksize == 3) DD_WGRAD(3); else DD_WGRAD(1);
+#undef DD_WGRAD
   }
   if (grad_x0 || grad_x1) {
     const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
@@ -550,8 +583,25 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     args.oy = reflect ? -1 : 0, args.ox = reflect ? -1 : 0;
     args.Cin = d->Cout, args.Cout = Cin;
     args.act = DD_ACT_NONE, args.out = gpad;
+    // zero padding (or 1x1) without up-sampling: the padded-grid gradient IS the input gradient, so the core
+    // writes grad_x0 / grad_x1 directly and the routing pass (and its round trip through HBM) disappears
+    const bool direct = !reflect && d->up0 == DD_UP_NONE;
+    if (direct) {
+      if (d->C1 > 0) {
+        args.out = grad_x0, args.out1 = grad_x1, args.split = d->C0;
+        if (grad_x0 == nullptr) {   // only the skip gradient is wanted: keep the kernel's primary pointer valid
+          args.out = gpad;          // scratch for the first C0 channels
+        }
+      } else {
+        args.out = grad_x0;
+      }
+    }
     rc = run_core(args, d->ksize, reinterpret_cast<float*>((char*)workspace + ws.wtd), d->weight, d->Cout, Cin, true, st);
     if (rc != DD_OK) return rc;
+    if (direct) {
+      DD_CHECK_CUDA(cudaGetLastError());
+      return DD_OK;
+    }
     RouteArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.gpad = gpad, ra.B = d->B, ra.Cin = Cin, ra.H = d->H, ra.W = d->W;
