@@ -1,0 +1,112 @@
+"""Host-side data-parallel logic (gradient arena + all-reduce) on CPU with the gloo backend, world size 2."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dd_b200.parallel import GradArena
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    shared = list(net.parameters())
+    arena = GradArena(shared + shared[:1], world_size=world)      # duplicate entry: shared encoder case
+    assert arena.numel == sum(p.numel() for p in shared)
+    x = torch.randn(5, 8, generator=torch.Generator().manual_seed(100 + rank))
+    net(x).pow(2).mean().backward()
+    assert arena.check_views(), "autograd must accumulate into the arena views in place"
+    local = arena.flat.clone()
+    arena.all_reduce()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    expect = torch.stack(gathered).mean(0)
+    ok = torch.allclose(arena.flat, expect, rtol=1e-6, atol=1e-8)
+    # a second backward keeps accumulating into the same storage after zero()
+    arena.zero()
+    net(x).pow(2).mean().backward()
+    ok = ok and arena.check_views() and torch.allclose(arena.flat, local, rtol=1e-6, atol=1e-8)
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_grad_arena_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    results = dict(out.get(timeout=10) for _ in range(2))
+    assert results == {0: True, 1: True}
+
+
+def test_grad_arena_single_process_is_noop():
+    from dd_b200.parallel import GradArena
+
+    w = torch.nn.Parameter(torch.ones(3, 3))
+    arena = GradArena([w], world_size=1)
+    (w * 2).sum().backward()
+    before = arena.flat.clone()
+    arena.all_reduce()
+    assert torch.equal(arena.flat, before) and torch.equal(w.grad, torch.full((3, 3), 2.0))
+
+
+def test_library_exports_every_declared_symbol():
+    """include/dynamo_b200.h <-> libdynamo_b200.so <-> ctypes signatures stay in sync (no compute calls)."""
+    import re
+    from dd_b200 import _lib
+
+    lib = _lib.load()
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dynamo_b200.h")).read()
+    declared = set(re.findall(r"\b(dd_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no entry points found in the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dynamo_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.dd_version() >= 100
+    assert set(_lib.SIGNATURES) <= declared
+
+
+def test_cpu_tensors_are_refused_by_every_op():
+    import tools
+    from dd_b200 import DynamoB200Error
+    from dd_b200 import functional as Fn
+
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(DynamoB200Error):
+        tools.SSIM()(x, x)
+    with pytest.raises(DynamoB200Error):
+        Fn.conv2d_fused(x, torch.rand(4, 3, 3, 3))
+    with pytest.raises(DynamoB200Error):
+        tools.BackprojectDepth(1, 8, 8)(torch.rand(1, 1, 8, 8), torch.eye(4)[None])
+    with pytest.raises(DynamoB200Error):
+        tools.compute_smooth_loss(x, x)
+
+
+def test_options_defaults_match_reference_surface():
+    import options
+
+    opt = options.DynamoOptions().parse(args=[])
+    assert (opt.dataset, opt.height, opt.width, opt.scales, opt.batch_size) == ("waymo", 320, 480, [0, 1, 2], 3)
+    assert opt.frame_ids == [0, -1, 1] and opt.epoch_schedules == [1, 1, 5, 20] and opt.epoch_size == 8000
+    opt = options.DynamoOptions().parse(args=["-d", "kitti", "--depth_model", "monodepthv2"])
+    assert (opt.height, opt.width, opt.scales, opt.split) == (192, 640, [0, 1, 2, 3], "eigen_zhou")
+    g = sorted(k for k in vars(opt) if k.startswith("g_"))
+    assert g == ["g_c_consistency", "g_c_smooth", "g_d_ground", "g_d_smooth", "g_m_smooth", "g_m_sparsity", "g_p_photo"]
