@@ -28,10 +28,12 @@ struct FwdArgs {
   int has_aux;
 };
 
-// shared memory carve-up (floats): Y[3][34][36] | X[2][3][34][36] | side[2][5][32][32] (flow modes)
+// shared memory carve-up (floats): Y[3][34][36] | X[2][3][34][36] | lo[2][5][16][16] (flow modes: low-resolution
+// accumulators of the 2^s-block centre averages, filled with shared-memory atomics)
 __device__ __forceinline__ float* smem_Y(float* s) { return s; }
 __device__ __forceinline__ float* smem_X(float* s, int f) { return s + 3 * PLANE1 * (1 + f); }
-__device__ __forceinline__ float* smem_side(float* s) { return s + 9 * PLANE1; }
+__device__ __forceinline__ float* smem_lo(float* s) { return s + 9 * PLANE1; }
+constexpr int LO_PLANE = (TILE / 2) * (TILE / 2);   // 256 low-res pixels per tile at level 1 (the largest staged level)
 
 struct SsimOut {
   float L[2][4];   // per frame, per row of the thread's 4-row run
@@ -109,7 +111,7 @@ __device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const f
 }
 
 template <int MODE, int F>
-__global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_fwd_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fwd_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ CamConst cam;
   __shared__ float red[WP_THREADS / 32][8];
@@ -147,6 +149,10 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_fwd_kernel(const __g
   }
   __syncthreads();
 
+  if (MODE >= 1) {
+    float* lo = smem_lo(smem);
+    for (int i = tid; i < 2 * 5 * LO_PLANE; i += WP_THREADS) lo[i] = 0.f;
+  }
   const float l1_w = 1.f - d.ssim_weight;
   SsimOut ident;
   if (automask) {   // identity reprojection losses (Trainer.py:327-333), level independent
@@ -160,6 +166,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_fwd_kernel(const __g
     const size_t p_lo = (size_t)h * w;
     const float* disp = d.disp[si] + (size_t)b * p_lo;
 
+    float s_cc[2] = {0.f, 0.f}, s_mag[2] = {0.f, 0.f};
     // ---- stage A: warp every halo pixel of both frames ---------------------------------------
     for (int i = tid; i < HALO1 * HALO1; i += WP_THREADS) {
       const int hr = i / HALO1, hc = i - hr * HALO1;
@@ -201,9 +208,28 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_fwd_kernel(const __g
         }
         if (interior) {
           if (MODE >= 1) {
-            float* side = smem_side(smem) + f * 5 * TILE * TILE + (hr - 1) * TILE + (hc - 1);
-            side[0] = g.res.x, side[TILE * TILE] = g.res.y, side[2 * TILE * TILE] = g.res.z;
-            side[3 * TILE * TILE] = g.dsx, side[4 * TILE * TILE] = g.dsy;
+            if (shift == 0) {   // level 0: the "down-sampled" by-products are the pixel's own values
+              const float mag = g.dsx * g.dsx + g.dsy * g.dsy;                 // Trainer.py:396
+              s_mag[f] += mag;
+              if (a.has_aux && a.aux.mag[si][f]) a.aux.mag[si][f][(size_t)b * P + o] = mag;
+              if (a.has_aux && a.aux.resid[si][f]) {
+                float* ro = a.aux.resid[si][f] + (size_t)b * 3 * P + o;
+                ro[0] = g.res.x, ro[P] = g.res.y, ro[2 * P] = g.res.z;
+              }
+              if (MODE == 2) {   // c_consistency (Trainer.py:384-386); at level 0 up(mask) == mask, up(disp) == disp
+                const float valid = __ldg(disp + o) > d.mask_disp_thrd ? 1.f : 0.f;
+                s_cc[f] += valid * (1.f - m) * (fabsf(g.res.x) + fabsf(g.res.y) + fabsf(g.res.z));
+              }
+            } else {             // levels > 0: bilinear down-sampling = mean of the 2x2 centre taps of each 2^s block
+              const int half = 1 << (shift - 1), msk = (1 << shift) - 1;
+              const int rr = r & msk, cr = c & msk;
+              if ((rr == half - 1 || rr == half) && (cr == half - 1 || cr == half)) {
+                const int tl = TILE >> shift;
+                float* lo = smem_lo(smem) + f * 5 * LO_PLANE + ((hr - 1) >> shift) * tl + ((hc - 1) >> shift);
+                atomicAdd(lo, 0.25f * g.res.x), atomicAdd(lo + LO_PLANE, 0.25f * g.res.y), atomicAdd(lo + 2 * LO_PLANE, 0.25f * g.res.z);
+                atomicAdd(lo + 3 * LO_PLANE, 0.25f * g.dsx), atomicAdd(lo + 4 * LO_PLANE, 0.25f * g.dsy);
+              }
+            }
           }
           if (a.has_aux) {
             if (a.aux.warped[si][f]) {
@@ -254,29 +280,22 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_fwd_kernel(const __g
       }
     }
 
-    // ---- stage C: low-resolution by-products of the scene-flow phases --------------------------
-    float s_cc[2] = {0.f, 0.f}, s_mag[2] = {0.f, 0.f};
-    if (MODE >= 1) {
-      const int tl = TILE >> shift;                    // low-res pixels per tile side
-      const int nc = shift == 0 ? 1 : 2;               // centre taps per axis (bilinear down-sampling)
-      const int off = shift == 0 ? 0 : (1 << (shift - 1)) - 1;
-      const float wgt = shift == 0 ? 1.f : 0.25f;
+    // ---- stage C: low-resolution by-products of the scene-flow phases (levels > 0) -----------------
+    if (MODE >= 1 && shift != 0) {
+      const int tl = TILE >> shift;
       for (int i = tid; i < tl * tl; i += WP_THREADS) {
         const int li = i / tl, lj = i - li * tl;
         const int gi = (r0 >> shift) + li, gj = (c0 >> shift) + lj;
         const size_t ol = (size_t)gi * w + gj;
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          const float* side = smem_side(smem) + f * 5 * TILE * TILE;
-          float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int dy = 0; dy < nc; ++dy)
-            for (int dx = 0; dx < nc; ++dx) {
-              const int q = ((li << shift) + off + dy) * TILE + (lj << shift) + off + dx;
+          float* lo = smem_lo(smem) + f * 5 * LO_PLANE + i;
+          float acc[5];
 #pragma unroll
-              for (int k = 0; k < 5; ++k) acc[k] += side[k * TILE * TILE + q];
-            }
-#pragma unroll
-          for (int k = 0; k < 5; ++k) acc[k] *= wgt;   // utils.interp down-sampling (Trainer.py:284,394-395)
+          for (int k = 0; k < 5; ++k) {
+            acc[k] = lo[k * LO_PLANE];
+            lo[k * LO_PLANE] = 0.f;          // ready for the next level
+          }
           const float mag = acc[3] * acc[3] + acc[4] * acc[4];          // Trainer.py:396
           s_mag[f] += mag;
           if (a.has_aux && a.aux.mag[si][f]) a.aux.mag[si][f][(size_t)b * p_lo + ol] = mag;
@@ -361,7 +380,7 @@ int warp_photo_fwd_impl(const dd_warp_desc* desc, const dd_warp_aux* aux, float*
   const int num_ctas = grid.x * grid.y * grid.z;
   const int mode = (desc->flags & DD_FLAG_CMPFLOW) ? ((desc->flags & DD_FLAG_MOTMASK) ? 2 : 1) : 0;
   size_t smem_bytes = 9 * PLANE1 * sizeof(float);
-  if (mode >= 1) smem_bytes += 2 * 5 * TILE * TILE * sizeof(float);
+  if (mode >= 1) smem_bytes += 2 * 5 * LO_PLANE * sizeof(float);
   const int F = desc->num_frames;
   if (mode == 0 && F == 2) rc = launch_fwd<0, 2>(args, grid, smem_bytes, st);
   else if (mode == 1 && F == 2) rc = launch_fwd<1, 2>(args, grid, smem_bytes, st);
