@@ -47,6 +47,53 @@ __device__ __forceinline__ float virt_load(const VirtIn& v, int b, int ci, int y
   return __ldg(v.x1 + (((size_t)b * v.C1 + (ci - v.C0)) * v.Hin + y) * v.Win + x);
 }
 
+// Per-CTA source map of one input tile: where every tile position reads from, independent of the channel.
+// Built once per CTA so the per-k-step staging is a table look-up + load instead of re-deriving padding,
+// reflection and up-sampling taps for every element of every channel.
+struct TapEntry {
+  int o00, o01, o10, o11;   // offsets inside one x0 channel plane (o00 < 0: zero padding / outside)
+  float ly, lx;             // bilinear weights (DD_UP_BILINEAR2 only)
+};
+
+__device__ __forceinline__ void build_tile_map(const VirtIn& v, int y, int x, TapEntry& e0, int& o1) {
+  e0.o00 = e0.o01 = e0.o10 = e0.o11 = -1;
+  e0.ly = e0.lx = 0.f;
+  o1 = -1;
+  if (y < -1 || y > v.Hin || x < -1 || x > v.Win) return;
+  if (v.pad_mode == DD_PAD_REFLECT) {
+    y = reflect1(y, v.Hin);
+    x = reflect1(x, v.Win);
+  } else if (y < 0 || y >= v.Hin || x < 0 || x >= v.Win) {
+    return;
+  }
+  o1 = y * v.Win + x;
+  if (v.up0 == DD_UP_NONE) {
+    e0.o00 = y * v.W0 + x;
+  } else if (v.up0 == DD_UP_NEAREST2) {
+    e0.o00 = (y >> 1) * v.W0 + (x >> 1);
+  } else {
+    const Taps ty = up_taps(y, 1, v.H0), tx = up_taps(x, 1, v.W0);
+    e0.o00 = ty.i0 * v.W0 + tx.i0, e0.o01 = ty.i0 * v.W0 + tx.i1;
+    e0.o10 = ty.i1 * v.W0 + tx.i0, e0.o11 = ty.i1 * v.W0 + tx.i1;
+    e0.ly = ty.l, e0.lx = tx.l;
+  }
+}
+
+__device__ __forceinline__ float map_load(const VirtIn& v, int b, int cg, const TapEntry* __restrict__ tab0,
+                                          const int* __restrict__ tab1, int pos) {
+  if (cg < v.C0) {
+    const TapEntry e = tab0[pos];
+    if (e.o00 < 0) return 0.f;
+    const float* p = v.x0 + ((size_t)b * v.C0 + cg) * v.H0 * v.W0;
+    if (v.up0 != DD_UP_BILINEAR2) return __ldg(p + e.o00);
+    const float v00 = __ldg(p + e.o00), v01 = __ldg(p + e.o01), v10 = __ldg(p + e.o10), v11 = __ldg(p + e.o11);
+    return (1.f - e.ly) * ((1.f - e.lx) * v00 + e.lx * v01) + e.ly * ((1.f - e.lx) * v10 + e.lx * v11);
+  }
+  const int o = tab1[pos];
+  if (o < 0) return 0.f;
+  return __ldg(v.x1 + ((size_t)b * v.C1 + (cg - v.C0)) * v.Hin * v.Win + o);
+}
+
 struct ConvArgs {
   VirtIn vin;
   int B, Ho, Wo;    // output grid
@@ -71,14 +118,19 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int KS, int CPT>
-__global__ void __launch_bounds__(CONV_THREADS) conv_core_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int KK = KS * KS;
   constexpr int HALO = KS / 2;
   constexpr int ROWS = CT_H + 2 * HALO, COLS = CT_W + 2 * HALO;
+  constexpr int NPOS = ROWS * COLS;
   constexpr int CO_T = 8 * CPT;
   constexpr int NV = 8 + KS - 1;
-  __shared__ __align__(16) float in_s[CI_T * IN_PLANE];
+  constexpr int N_IN = CI_T * NPOS;
+  constexpr int NPRE = (N_IN + CONV_THREADS - 1) / CONV_THREADS;
+  __shared__ __align__(16) float in_s[2][CI_T * IN_PLANE];
   __shared__ __align__(16) float w_s[CI_T * KK * CO_T];
+  __shared__ TapEntry tab0[NPOS];
+  __shared__ int tab1[NPOS];
 
   const int tid = threadIdx.x;
   const int pg = tid & 15, cg = tid >> 4;
@@ -88,51 +140,79 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_core_kernel(const __grid_co
   const int co0 = blockIdx.y * CO_T;
   const int b = blockIdx.z;
 
+  for (int i = tid; i < NPOS; i += CONV_THREADS) {
+    const int r = i / COLS, c = i - r * COLS;
+    build_tile_map(a.vin, ty0 + r - HALO + a.oy, tx0 + c - HALO + a.ox, tab0[i], tab1[i]);
+  }
+
   float acc[CPT][8];
 #pragma unroll
   for (int c = 0; c < CPT; ++c)
 #pragma unroll
     for (int p = 0; p < 8; ++p) acc[c][p] = 0.f;
 
-  for (int ci0 = 0; ci0 < a.Cin; ci0 += CI_T) {
-    // stage the virtual-input tile
-    for (int i = tid; i < CI_T * ROWS * COLS; i += CONV_THREADS) {
-      const int ci = i / (ROWS * COLS);
-      const int rem = i - ci * (ROWS * COLS);
-      const int r = rem / COLS, c = rem - r * COLS;
+  // tile-position -> shared-memory offset of this thread's staging slots (k-step invariant)
+  auto gather = [&](int ci0, float (&pre)[NPRE]) {
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int i = tid + j * CONV_THREADS;
       float v = 0.f;
-      if (ci0 + ci < a.Cin) v = virt_load(a.vin, b, ci0 + ci, ty0 + r - HALO + a.oy, tx0 + c - HALO + a.ox);
-      in_s[ci * IN_PLANE + r * IN_PITCH + c] = v;
+      if (i < N_IN) {
+        const int ci = i / NPOS, pos = i - ci * NPOS;
+        if (ci0 + ci < a.Cin) v = map_load(a.vin, b, ci0 + ci, tab0, tab1, pos);
+      }
+      pre[j] = v;
     }
-    // stage the weights [ci][tap][co]
-    for (int i = tid; i < CI_T * KK * (CO_T / 4 > 0 ? CO_T / 4 : 1); i += CONV_THREADS) {
-      const int per = CO_T / 4;
-      const int q = i % per, ct = i / per;   // ct = ci*KK + tap
+  };
+  auto scatter = [&](int buf, const float (&pre)[NPRE]) {
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int i = tid + j * CONV_THREADS;
+      if (i < N_IN) {
+        const int ci = i / NPOS, pos = i - ci * NPOS;
+        const int r = pos / COLS, c = pos - r * COLS;
+        in_s[buf][ci * IN_PLANE + r * IN_PITCH + c] = pre[j];
+      }
+    }
+  };
+  auto stage_weights = [&](int ci0) {
+    constexpr int PER = CO_T / 4;
+    for (int i = tid; i < CI_T * KK * PER; i += CONV_THREADS) {
+      const int q = i % PER, ct = i / PER;   // ct = ci*KK + tap
       const int ci = ct / KK;
       float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ci0 + ci < a.Cin)
         w4 = __ldg(reinterpret_cast<const float4*>(a.wt + ((size_t)(ci0 * KK + ct)) * a.cout_pad + co0 + q * 4));
-      reinterpret_cast<float4*>(w_s)[ct * per + q] = w4;
+      reinterpret_cast<float4*>(w_s)[ct * PER + q] = w4;
     }
-    __syncthreads();
+  };
 
-#pragma unroll 2
+  float pre[NPRE];
+  __syncthreads();   // tile map complete
+  gather(0, pre);
+  scatter(0, pre);
+
+  const int nk = (a.Cin + CI_T - 1) / CI_T;
+  for (int k = 0; k < nk; ++k) {
+    const int buf = k & 1;
+    stage_weights(k * CI_T);
+    __syncthreads();   // in_s[buf] and w_s of step k are visible
+    if (k + 1 < nk) gather((k + 1) * CI_T, pre);   // loads in flight during the FMAs below
+    const float* in_b = in_s[buf];
+#pragma unroll 1
     for (int ci = 0; ci < CI_T; ++ci) {
-      const float* ip = in_s + ci * IN_PLANE + row * IN_PITCH + seg * 8;
-      float iv[KS][NV];
+      const float* ip = in_b + ci * IN_PLANE + row * IN_PITCH + seg * 8;
 #pragma unroll
       for (int dy = 0; dy < KS; ++dy) {
+        float iv[NV];
         const float4 v0 = *reinterpret_cast<const float4*>(ip + dy * IN_PITCH);
         const float4 v1 = *reinterpret_cast<const float4*>(ip + dy * IN_PITCH + 4);
-        iv[dy][0] = v0.x, iv[dy][1] = v0.y, iv[dy][2] = v0.z, iv[dy][3] = v0.w;
-        iv[dy][4] = v1.x, iv[dy][5] = v1.y, iv[dy][6] = v1.z, iv[dy][7] = v1.w;
+        iv[0] = v0.x, iv[1] = v0.y, iv[2] = v0.z, iv[3] = v0.w;
+        iv[4] = v1.x, iv[5] = v1.y, iv[6] = v1.z, iv[7] = v1.w;
         if (KS == 3) {
           const float2 v2 = *reinterpret_cast<const float2*>(ip + dy * IN_PITCH + 8);
-          iv[dy][NV - 2] = v2.x, iv[dy][NV - 1] = v2.y;
+          iv[NV - 2] = v2.x, iv[NV - 1] = v2.y;
         }
-      }
-#pragma unroll
-      for (int dy = 0; dy < KS; ++dy)
 #pragma unroll
         for (int dx = 0; dx < KS; ++dx) {
           const float* wp = w_s + (ci * KK + dy * KS + dx) * CO_T + cg * CPT;
@@ -150,10 +230,12 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_core_kernel(const __grid_co
 #pragma unroll
           for (int c = 0; c < CPT; ++c)
 #pragma unroll
-            for (int p = 0; p < 8; ++p) acc[c][p] = fmaf(wv[c], iv[dy][p + dx], acc[c][p]);
+            for (int p = 0; p < 8; ++p) acc[c][p] = fmaf(wv[c], iv[p + dx], acc[c][p]);
         }
+      }
     }
-    __syncthreads();
+    if (k + 1 < nk) scatter(buf ^ 1, pre);   // other buffer: nobody reads it during this step
+    __syncthreads();                         // all reads of w_s / in_s[buf] done before they are overwritten
   }
 
   // epilogue: bias, activation, residual, store
@@ -308,11 +390,17 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   constexpr int HALO = KS / 2;
   constexpr int ROWS = CT_H + 2 * HALO, COLS = CT_W + 2 * HALO;
   constexpr int CO_T = 16 * WCO;
+  constexpr int NPOS = ROWS * COLS;
   __shared__ __align__(16) float g_s[CO_T * WG_GPITCH];
   __shared__ __align__(16) float v_s[CI_T * IN_PLANE];
+  __shared__ TapEntry tab0[NPOS];
+  __shared__ int tab1[NPOS];
 
   const int tid = threadIdx.x;
-  const int ci = tid & 7, cq = tid >> 3;   // output channels co0 + cq*WCO .. +WCO-1, input channel ci0 + ci
+  // warp = 16 output-channel lanes x 2 input channels: the input-tile loads are (almost) warp-uniform broadcasts and
+  // the gradient-tile loads of the 16 lanes fall into distinct banks (channel stride 132 floats); thread owns output
+  // channels co0 + cq + 16*c (c < WCO) and input channel ci0 + ci
+  const int cq = tid & 15, ci = ((tid >> 5) << 1) + ((tid >> 4) & 1);
   const int co0 = blockIdx.x * CO_T, ci0 = blockIdx.y * CI_T;
   const int n_tiles = a.tiles_x * a.tiles_y;
   const int n_items = a.B * n_tiles;
@@ -348,23 +436,27 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
       }
       *reinterpret_cast<float4*>(g_s + c * WG_GPITCH + r * CT_W + 4 * q) = v;
     }
-    for (int i = tid; i < CI_T * ROWS * COLS; i += CONV_THREADS) {
-      const int c = i / (ROWS * COLS);
-      const int rem = i - c * (ROWS * COLS);
-      const int r = rem / COLS, cc = rem - r * COLS;
+    for (int i = tid; i < NPOS; i += CONV_THREADS) {
+      const int r = i / COLS, cc = i - r * COLS;
+      build_tile_map(a.vin, ty0 + r - HALO, tx0 + cc - HALO, tab0[i], tab1[i]);
+    }
+    __syncthreads();
+    for (int i = tid; i < CI_T * NPOS; i += CONV_THREADS) {
+      const int c = i / NPOS, pos = i - c * NPOS;
+      const int r = pos / COLS, cc = pos - r * COLS;
       float v = 0.f;
-      if (ci0 + c < a.Cin) v = virt_load(a.vin, b, ci0 + c, ty0 + r - HALO, tx0 + cc - HALO);
+      if (ci0 + c < a.Cin) v = map_load(a.vin, b, ci0 + c, tab0, tab1, pos);
       v_s[c * IN_PLANE + r * IN_PITCH + cc] = v;
     }
     __syncthreads();
-#pragma unroll 2
+#pragma unroll 1
     for (int r = 0; r < CT_H; ++r) {
 #pragma unroll
       for (int xq = 0; xq < CT_W; xq += 4) {
         float gv[WCO][4];
 #pragma unroll
         for (int c = 0; c < WCO; ++c) {
-          const float4 g4 = *reinterpret_cast<const float4*>(g_s + (cq * WCO + c) * WG_GPITCH + r * CT_W + xq);
+          const float4 g4 = *reinterpret_cast<const float4*>(g_s + (cq + 16 * c) * WG_GPITCH + r * CT_W + xq);
           gv[c][0] = g4.x, gv[c][1] = g4.y, gv[c][2] = g4.z, gv[c][3] = g4.w;
         }
 #pragma unroll
@@ -391,7 +483,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   if (ci0 + ci < a.Cin) {
 #pragma unroll
     for (int c = 0; c < WCO; ++c) {
-      const int co = co0 + cq * WCO + c;
+      const int co = co0 + cq + 16 * c;
       if (co >= a.Cout) continue;
 #pragma unroll
       for (int t = 0; t < KK; ++t) atomicAdd(a.gw + ((size_t)co * a.Cin + ci0 + ci) * KK + t, acc[c][t]);
