@@ -113,6 +113,7 @@ SIGNATURES = {
     "dd_project_bwd": (C.c_int, [FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
     "dd_ssim_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_ssim_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_ground_score": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, FP, FP]),
 }
 
 _lib = None

@@ -586,3 +586,17 @@ def ssim(x, y):
     if not x.is_cuda:
         raise L.DynamoB200Error("ssim needs CUDA tensors (no CPU fallback)")
     return _SsimFn.apply(_prep(x), _prep(y))
+
+
+def ground_score(points, w, row0, tol):
+    """counts (K,) int32 of ground points within `tol` of each plane hypothesis (tools.py:113-139); no gradient."""
+    if not points.is_cuda:
+        raise L.DynamoB200Error("ground_score needs CUDA tensors (no CPU fallback)")
+    lib = L.load()
+    points, w = _prep(points.detach()), _prep(w.detach().reshape(-1, 3))
+    B, _, H, W = points.shape
+    K = w.shape[0]
+    counts = torch.empty(K, dtype=torch.int32, device=points.device)
+    L.check(lib.dd_ground_score(points.data_ptr(), w.data_ptr(), B, H, W, int(row0), K, float(tol), counts.data_ptr(), _stream()),
+            "dd_ground_score")
+    return counts

@@ -118,8 +118,9 @@ class DepthMetrics(nn.Module):
 
 class GroundPlane(nn.Module):
     """RANSAC ground-plane fit used by the d_ground prior in phase fine_tune (reference: tools.py:76-164).
-    SURVEY 8f-1 ("next"): still host-driven torch code (numpy RNG for hypothesis sampling, injectable
-    through `rand_index_fn` for parity tests); a fused scoring kernel is the follow-up."""
+    Hypothesis sampling keeps the reference's host numpy RNG (injectable through `rand_index_fn` for parity
+    tests); the hypothesis scoring -- B*max_it planes against 0.4*H*W points, a 1.9 GB intermediate at bs32 in
+    the reference -- is one dd_ground_score launch that reads every point once per 20 hypotheses."""
 
     def __init__(self, num_points_per_it=5, max_it=25, tol=0.1, g_prior=0.5, vertical_axis=1, rand_index_fn=None):
         super().__init__()
@@ -137,6 +138,21 @@ class GroundPlane(nn.Module):
         A, rhs = self._design(pts)
         return A @ param - rhs
 
+    def estimate_ground_plane_fused(self, points, row0):
+        """points (B,3,H,W) on the GPU; same result as estimate_ground_plane on points[:, :, row0:, :]."""
+        B, _, H, W = points.shape
+        N = (H - row0) * W
+        k = self.num_points_per_it * self.max_it
+        flat = points[:, :, row0:, :].reshape(B, 3, N)
+        idx = torch.from_numpy(np.stack([np.asarray(self.rand_index_fn(N, k)) for _ in range(B)])).to(points.device)
+        picks = torch.gather(flat, 2, idx.unsqueeze(1).expand(B, 3, k)).permute(0, 2, 1)        # (B, k, 3)
+        A, rhs = self._design(picks.reshape(-1, self.num_points_per_it, 3))
+        At = A.transpose(2, 1)
+        ws = (torch.inverse(At @ A + 1e-6) @ At @ rhs).reshape(-1, 3)                          # (B*max_it, 3)
+        counts = _F.ground_score(points, ws, row0, self.tol).reshape(B, self.max_it)
+        best = counts.argmax(1)
+        return ws.reshape(B, self.max_it, 3, 1)[torch.arange(B, device=points.device), best]
+
     def estimate_ground_plane(self, pts):
         B, N, _ = pts.shape
         k = self.num_points_per_it * self.max_it
@@ -153,7 +169,10 @@ class GroundPlane(nn.Module):
 
     def forward(self, points):
         B, _, H, W = points.shape
-        ground = points[:, :, -int(self.g_prior * H):, :].reshape(B, 3, -1).permute(0, 2, 1)
-        param = self.estimate_ground_plane(ground)
+        if points.is_cuda and self.vertical_axis == 1:
+            param = self.estimate_ground_plane_fused(points.detach().contiguous(), H - int(self.g_prior * H))
+        else:
+            ground = points[:, :, -int(self.g_prior * H):, :].reshape(B, 3, -1).permute(0, 2, 1)
+            param = self.estimate_ground_plane(ground)
         dist = self.dist_from_plane(points.reshape(B, 3, H * W).permute(0, 2, 1), param).permute(0, 2, 1).reshape(B, 1, H, W)
         return dist.detach(), param.detach()

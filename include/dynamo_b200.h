@@ -227,6 +227,16 @@ int dd_ssim_fwd(const float* x, const float* y, int BC, int H, int W, float* out
 /* gradient w.r.t. x (SSIM is symmetric: swap x and y for the gradient w.r.t. y) */
 int dd_ssim_bwd(const float* x, const float* y, const float* grad_out, int BC, int H, int W, float* grad_x, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * RANSAC ground-plane hypothesis scoring (tools.GroundPlane.estimate_ground_plane, tools.py:113-139)
+ *   counts[k] = #{ n : | x_n*w[k][0] + z_n*w[k][1] + w[k][2] - y_n | < tol }  over the ground rows
+ *   (row >= row0) of image (k % B) -- the reference pairs hypothesis k with image k % B because it tiles
+ *   the points with .repeat(max_it,1,1) (tools.py:131); reproduced as is.  Reads every point once per
+ *   20 hypotheses instead of materialising the (B*max_it, N, 3) tensor (1.9 GB at bs32, 192x640).
+ * ------------------------------------------------------------------------------------------ */
+int dd_ground_score(const float* points /* (B,3,H,W) */, const float* w /* (K,3), K = B*max_it */, int B, int H, int W,
+                    int row0, int K, float tol, int32_t* counts /* (K) overwritten */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,17 +44,20 @@ LOSS_CASES = [
     dict(name="loss_maskinit_lite_32x64", model="litemono", phase="mask_init", B=2, H=32, W=64, ts="ones", step=20, full=True, seed=13),
     dict(name="loss_finetune_md2_64x96", model="monodepthv2", phase="fine_tune", B=3, H=64, W=96, ts="float", step=50, full=False, seed=14),
     dict(name="loss_dispinit_lite_96x128", model="litemono", phase="disp_init", B=2, H=96, W=128, ts="ones", step=0, full=False, seed=15),
+    # fine_tune with the RANSAC ground prior on (g_d_ground = 0.1); host RNG replaced by oracle.ground.SeededIndices
+    dict(name="loss_finetune_ground_lite_64x96", model="litemono", phase="fine_tune", B=3, H=64, W=96, ts="ones", step=60, full=False,
+         seed=16, ground=True),
 ]
 
 
 def run_reference_loss(ns, case):
     argv = ["-d", "kitti", "--depth_model", case["model"], "--weights_init", "scratch", "-b", str(case["B"]),
-            "--height", str(case["H"]), "--width", str(case["W"]), "--g_d_ground", "0.0"]
+            "--height", str(case["H"]), "--width", str(case["W"]), "--g_d_ground", "0.1" if case.get("ground") else "0.0"]
     tr = _refshim.make_reference_trainer(ns, argv, phase=case["phase"], step=case["step"], steps_per_epoch=100)
     scales = tr.opt.scales
     flow = case["phase"] != "disp_init"
     inputs, leaves = synth.make_loss_inputs(case["seed"], case["B"], case["H"], case["W"], scales, kind="kitti",
-                                            flow=flow, ts_mode=case["ts"])
+                                            flow=flow, ts_mode=case["ts"], all_scale_intrinsics=bool(case.get("ground")))
     tr.apply_img_resize(inputs)  # Trainer.py:729-734 builds ('color',0,s) for s>0
     noise = synth.automask_noise(case["seed"], case["B"], case["H"], case["W"], scales)
 
@@ -80,12 +83,18 @@ def run_reference_loss(ns, case):
     def fake_randn(*a, **kw):
         return noise_queue.pop(0).clone()
 
+    real_choice = np.random.choice
+    if case.get("ground"):
+        from .ground import SeededIndices
+        seeded = SeededIndices(case["seed"])
+        np.random.choice = lambda a, size, replace=True: seeded(len(a), size)
     torch.randn = fake_randn
     try:
         tr.generate_images_pred(inputs, outputs)
         losses = tr.compute_losses(inputs, outputs)
     finally:
         torch.randn = real_randn
+        np.random.choice = real_choice
     losses["loss"].backward()
 
     rec = {}
@@ -105,6 +114,7 @@ def run_reference_loss(ns, case):
     rec["meta:seed"] = np.asarray(case["seed"])
     rec["meta:ts_mode"] = np.asarray(case["ts"])
     rec["meta:shape"] = np.asarray([case["B"], case["H"], case["W"]])
+    rec["meta:ground"] = np.asarray(1 if case.get("ground") else 0)
     for k, v in losses.items():
         rec["loss:" + key_str(k)] = np.float64(float(v))
     for k, v in grads_of.items():

@@ -35,6 +35,8 @@ class LossCase:
         self.steps_per_epoch = int(z["meta:steps_per_epoch"])
         self.B, self.H, self.W = (int(v) for v in z["meta:shape"])
         seed = int(z["meta:seed"])
+        self.seed = seed
+        self.ground = bool(int(z["meta:ground"])) if "meta:ground" in z.files else False
         ts_mode = str(z["meta:ts_mode"])
         have_inputs = any(k.startswith("in:") for k in z.files)
         if have_inputs:
@@ -43,7 +45,8 @@ class LossCase:
             self.noise = {int(k[6:]): torch.from_numpy(z[k]) for k in z.files if k.startswith("noise:")}
         else:
             self.inputs, self.leaves = synth.make_loss_inputs(seed, self.B, self.H, self.W, self.scales, kind="kitti",
-                                                              flow=self.phase != "disp_init", ts_mode=ts_mode)
+                                                              flow=self.phase != "disp_init", ts_mode=ts_mode,
+                                                              all_scale_intrinsics=self.ground)
             synth.add_color_pyramid(self.inputs, self.scales, self.H, self.W)
             self.noise = synth.automask_noise(seed, self.B, self.H, self.W, self.scales)
         # verify (re-)synthesised inputs against the recorded checksums
@@ -61,7 +64,7 @@ class LossCase:
         self.losses = {k[5:]: float(z[k]) for k in z.files if k.startswith("loss:")}
         self.grads = {parse_key(k[5:]): torch.from_numpy(z[k]) for k in z.files if k.startswith("grad:")}
         self.outputs = {parse_key(k[4:]): torch.from_numpy(z[k]) for k in z.files if k.startswith("out:")}
-        self.cfg = LossConfig(self.H, self.W, self.scales, phase=self.phase, g_d_ground=0.0)
+        self.cfg = LossConfig(self.H, self.W, self.scales, phase=self.phase, g_d_ground=0.1 if self.ground else 0.0)
 
     def fresh_outputs(self, dtype=torch.float32, device="cpu"):
         """outputs dict as Model.forward would fill it; returns (outputs, leaf dict with requires_grad)."""
@@ -94,4 +97,5 @@ LOSS_CASE_NAMES = [
     "loss_maskinit_lite_32x64",
     "loss_finetune_md2_64x96",
     "loss_dispinit_lite_96x128",
+    "loss_finetune_ground_lite_64x96",
 ]

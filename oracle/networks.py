@@ -193,6 +193,8 @@ class OracleTrainer:
         self.lr = learning_rate
         self.step, self.steps_per_epoch = 0, 100
         self.optimizer = None
+        # host RNG of the RANSAC ground prior (tools.py:126); replace for reproducible runs
+        self.rand_index_fn = lambda n, k: np.random.choice(np.arange(n), k, replace=True)
 
     def setup_phase(self, phase):
         self.cfg.set_phase(phase)
@@ -206,7 +208,11 @@ class OracleTrainer:
         if noise is None and self.cfg.automask:
             B = inputs[("color", 0, 0)].shape[0]
             noise = {s: torch.randn(B, len(self.cfg.frame_ids) - 1, self.cfg.height, self.cfg.width) for s in self.cfg.scales}
-        losses = vs.compute_losses(self.cfg, inputs, outputs, self.step, self.steps_per_epoch, noise=noise)
+        ground_fn = None
+        if self.cfg.g["d_ground"] > 0 and self.cfg.bool_MotMask and "Depth" in self.cfg.network_names:
+            from .ground import make_ground_fn
+            ground_fn = make_ground_fn(self.cfg, self.rand_index_fn)
+        losses = vs.compute_losses(self.cfg, inputs, outputs, self.step, self.steps_per_epoch, noise=noise, ground_fn=ground_fn)
         return outputs, losses
 
     def train_step(self, inputs, noise=None):

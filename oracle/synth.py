@@ -77,7 +77,7 @@ def pose_matrix(axisangle, translation):
 
 
 def make_loss_inputs(seed, batch, height, width, scales, kind="kitti", flow=True, ts_mode="ones",
-                     frame_ids=(0, -1, 1)):
+                     frame_ids=(0, -1, 1), all_scale_intrinsics=False):
     """Returns (inputs, leaves): `inputs` as the data loader would deliver them (without the colour
     pyramid of scales>0, see `add_color_pyramid`), `leaves` = network-output tensors of the keys
     Model.forward produces (disp, cam_T_cam, complete_flow, motion_prob)."""
@@ -93,6 +93,10 @@ def make_loss_inputs(seed, batch, height, width, scales, kind="kitti", flow=True
         inputs[("color_aug", f, 0)] = inputs[("color", f, 0)]
     K, inv_K = intrinsics(kind, height, width, batch)
     inputs[("K", 0)], inputs[("inv_K", 0)] = K, inv_K
+    if all_scale_intrinsics:   # datasets/base_dataset.py:154-163 provides K / inv_K for every pyramid level
+        for s in scales:
+            if s != 0:
+                inputs[("K", s)], inputs[("inv_K", s)] = intrinsics(kind, height // 2**s, width // 2**s, batch)
     for f in frame_ids[1:]:
         if ts_mode == "ones":
             inputs[("ts", f)] = torch.ones(batch, dtype=torch.int64)

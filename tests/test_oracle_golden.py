@@ -13,7 +13,11 @@ def run_oracle(case, dtype=torch.float32):
     inputs = case.cast_inputs(dtype)
     outputs, leaves = case.fresh_outputs(dtype)
     vs.generate_images_pred(case.cfg, inputs, outputs)
-    losses = vs.compute_losses(case.cfg, inputs, outputs, case.step, case.steps_per_epoch, noise=case.noise)
+    ground_fn = None
+    if case.ground:
+        from oracle.ground import SeededIndices, make_ground_fn
+        ground_fn = make_ground_fn(case.cfg, SeededIndices(case.seed))
+    losses = vs.compute_losses(case.cfg, inputs, outputs, case.step, case.steps_per_epoch, noise=case.noise, ground_fn=ground_fn)
     losses["loss"].backward()
     return outputs, leaves, losses
 
