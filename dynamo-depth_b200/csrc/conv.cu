@@ -9,6 +9,7 @@
 // The data gradient reuses the same core on the (zero-extended) output gradient with flipped,
 // transposed weights, producing the gradient on the padded grid; a light routing kernel then folds
 // the reflection border back and transposes the up-sampling / concatenation.
+#include <stdlib.h>
 #include <string.h>
 
 #include "dd_common.cuh"
@@ -370,6 +371,244 @@ __global__ void conv_route_kernel(const __grid_constant__ RouteArgs a) {
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int nbytes = valid ? 16 : 0;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(nbytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+// ---- Winograd F(2x2, 3x3) core (fp32, CUDA cores) -------------------------------------------------
+// 2.25x fewer multiply-adds than the direct form for the 3x3 layers: per CTA 8x16 output pixels = 32 tiles of
+// 2x2, 32 output channels, K-steps of 8 input channels.  Each step transforms the staged input tile
+// (V = B^T d B, 16 frequency planes) and runs 16 independent [32 co x 8 ci] x [8 ci x 32 tiles] products,
+// thread = (frequency, 8 channels, 8 tiles); the epilogue applies Y = A^T m A through shared memory.
+// Weights arrive pre-transformed (U = G g G^T) as wt[16][Cin][cout_pad].
+constexpr int WN_THREADS = 256;
+constexpr int WN_CO = 32;
+constexpr int WN_TILES = 32;
+constexpr int WN_VP = 36;    // V_s pitch over tiles
+constexpr int WN_MP = 33;    // M_s pitch over tiles
+constexpr int WN_SMEM_LOOP = 2 * CI_T * IN_PLANE + 16 * CI_T * WN_VP + 2 * 16 * CI_T * WN_CO;
+constexpr int WN_SMEM_EPI = 16 * WN_CO * WN_MP;
+constexpr int WN_SMEM_FLOATS = WN_SMEM_LOOP > WN_SMEM_EPI ? WN_SMEM_LOOP : WN_SMEM_EPI;
+
+__device__ __forceinline__ void emit_output(const ConvArgs& a, int b, int co, int y, int x, float v) {
+  if (y >= a.Ho || x >= a.Wo || co >= a.Cout) return;
+  v = apply_act(v + (a.bias ? __ldg(a.bias + co) : 0.f), a.act);
+  float* outp = a.out;
+  size_t o = (((size_t)b * a.Cout + co) * a.Ho + y) * a.Wo + x;
+  if (a.split > 0) {
+    if (co < a.split) o = (((size_t)b * a.split + co) * a.Ho + y) * a.Wo + x;
+    else outp = a.out1, o = (((size_t)b * (a.Cout - a.split) + (co - a.split)) * a.Ho + y) * a.Wo + x;
+    if (outp == nullptr) return;
+  }
+  if (a.residual) v += __ldg(a.residual + o);
+  outp[o] = v;
+}
+
+__global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int ROWS = CT_H + 2, COLS = CT_W + 2, NPOS = ROWS * COLS;
+  constexpr int N_IN = CI_T * NPOS;
+  constexpr int NPRE = (N_IN + WN_THREADS - 1) / WN_THREADS;
+  extern __shared__ __align__(16) float wsm[];
+  float* in_s = wsm;                                  // [2][CI_T*IN_PLANE]
+  float* V_s = wsm + 2 * CI_T * IN_PLANE;             // [16][CI_T][WN_VP]
+  float* U_s = V_s + 16 * CI_T * WN_VP;               // [2][16][CI_T][WN_CO], filled by cp.async one step ahead
+  float* M_s = wsm;                                   // epilogue only: [16][WN_CO][WN_MP]
+  __shared__ TapEntry tab0[NPOS];
+  __shared__ int tab1[NPOS];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const int ty0 = (tile / a.tiles_x) * CT_H, tx0 = (tile % a.tiles_x) * CT_W;
+  const int co0 = blockIdx.y * WN_CO;
+  const int b = blockIdx.z;
+  // GEMM role: frequency p, 8 output channels (cg), 8 tiles (tg)
+  const int p = 2 * warp + (lane >> 4), cg = (lane >> 2) & 3, tg = lane & 3;
+  // transform role: input channel ti, winograd tile tt
+  const int ti = tid >> 5, tt = tid & 31, ttr = tt >> 3, ttc = tt & 7;
+
+  for (int i = tid; i < NPOS; i += WN_THREADS) {
+    const int r = i / COLS, c = i - r * COLS;
+    build_tile_map(a.vin, ty0 + r - 1 + a.oy, tx0 + c - 1 + a.ox, tab0[i], tab1[i]);
+  }
+  float acc[8][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[c][t] = 0.f;
+
+  auto gather = [&](int ci0, float (&pre)[NPRE]) {
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int i = tid + j * WN_THREADS;
+      float v = 0.f;
+      if (i < N_IN) {
+        const int ci = i / NPOS, pos = i - ci * NPOS;
+        if (ci0 + ci < a.Cin) v = map_load(a.vin, b, ci0 + ci, tab0, tab1, pos);
+      }
+      pre[j] = v;
+    }
+  };
+  auto scatter = [&](int buf, const float (&pre)[NPRE]) {
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int i = tid + j * WN_THREADS;
+      if (i < N_IN) {
+        const int ci = i / NPOS, pos = i - ci * NPOS;
+        const int r = pos / COLS, c = pos - r * COLS;
+        in_s[buf * CI_T * IN_PLANE + ci * IN_PLANE + r * IN_PITCH + c] = pre[j];
+      }
+    }
+  };
+
+  auto issue_weights = [&](int ci0, int buf) {   // U_s[buf][p][ci][co] <- wt[p][ci0+ci][co0 + co]
+    for (int i = tid; i < 16 * CI_T * (WN_CO / 4); i += WN_THREADS) {
+      const int q = i & 7, pc = i >> 3;   // pc = p*CI_T + ci
+      const int pp = pc >> 3, ci = pc & 7;
+      const bool ok = ci0 + ci < a.Cin;
+      const float* src = a.wt + ((size_t)pp * a.Cin + (ok ? ci0 + ci : 0)) * a.cout_pad + co0 + q * 4;
+      cp_async16(U_s + buf * 16 * CI_T * WN_CO + i * 4, src, ok);
+    }
+    cp_async_commit();
+  };
+
+  float pre[NPRE];
+  __syncthreads();   // tile map complete
+  issue_weights(0, 0);
+  gather(0, pre);
+  scatter(0, pre);
+  cp_async_wait_all();
+  __syncthreads();
+
+  const int nk = (a.Cin + CI_T - 1) / CI_T;
+  for (int k = 0; k < nk; ++k) {
+    const int buf = k & 1;
+    // input transform V = B^T d B of (channel ti, tile tt)
+    {
+      const float* dp = in_s + buf * CI_T * IN_PLANE + ti * IN_PLANE + (2 * ttr) * IN_PITCH + 2 * ttc;
+      float d[4][4], t[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 lo = *reinterpret_cast<const float2*>(dp + i * IN_PITCH);
+        const float2 hi = *reinterpret_cast<const float2*>(dp + i * IN_PITCH + 2);
+        d[i][0] = lo.x, d[i][1] = lo.y, d[i][2] = hi.x, d[i][3] = hi.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[0][j] = d[0][j] - d[2][j];
+        t[1][j] = d[1][j] + d[2][j];
+        t[2][j] = d[2][j] - d[1][j];
+        t[3][j] = d[1][j] - d[3][j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float* vp = V_s + ((i * 4) * CI_T + ti) * WN_VP + tt;
+        vp[0 * CI_T * WN_VP] = t[i][0] - t[i][2];
+        vp[1 * CI_T * WN_VP] = t[i][1] + t[i][2];
+        vp[2 * CI_T * WN_VP] = t[i][2] - t[i][1];
+        vp[3 * CI_T * WN_VP] = t[i][1] - t[i][3];
+      }
+    }
+    __syncthreads();   // V_s of step k visible (U_s[buf] landed before the previous barrier)
+    if (k + 1 < nk) {
+      issue_weights((k + 1) * CI_T, buf ^ 1);
+      gather((k + 1) * CI_T, pre);
+    }
+    {
+      const float* up = U_s + buf * 16 * CI_T * WN_CO + p * CI_T * WN_CO + cg * 8;
+      const float* vp = V_s + p * CI_T * WN_VP + tg * 8;
+#pragma unroll 2
+      for (int ci = 0; ci < CI_T; ++ci) {
+        const float4 u0 = *reinterpret_cast<const float4*>(up + ci * WN_CO), u1 = *reinterpret_cast<const float4*>(up + ci * WN_CO + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(vp + ci * WN_VP), v1 = *reinterpret_cast<const float4*>(vp + ci * WN_VP + 4);
+        const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int tq = 0; tq < 8; ++tq) acc[c][tq] = fmaf(u[c], v[tq], acc[c][tq]);
+      }
+    }
+    if (k + 1 < nk) {
+      scatter(buf ^ 1, pre);
+      cp_async_wait_all();
+    }
+    __syncthreads();   // GEMM reads of U_s[buf] / V_s done; in_s[buf^1], U_s[buf^1] complete
+  }
+
+  // epilogue: gather the 16 frequencies of every (channel, tile) through shared memory, Y = A^T m A
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int tq = 0; tq < 8; ++tq) M_s[(p * WN_CO + cg * 8 + c) * WN_MP + tg * 8 + tq] = acc[c][tq];
+  __syncthreads();
+  for (int q = tid; q < WN_CO * WN_TILES; q += WN_THREADS) {
+    const int col = q >> 5, tl = q & 31;
+    const int tr = tl >> 3, tc = tl & 7;
+    float m[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[i][j] = M_s[((i * 4 + j) * WN_CO + col) * WN_MP + tl];
+    float sr[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sr[0][j] = m[0][j] + m[1][j] + m[2][j];
+      sr[1][j] = m[1][j] - m[2][j] - m[3][j];
+    }
+    const int y = ty0 + 2 * tr, x = tx0 + 2 * tc, co = co0 + col;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      emit_output(a, b, co, y + i, x, sr[i][0] + sr[i][1] + sr[i][2]);
+      emit_output(a, b, co, y + i, x + 1, sr[i][1] - sr[i][2] - sr[i][3]);
+    }
+  }
+}
+
+// U = G g G^T for every (co, ci): wt[16][Cin'][out_pad]; `transpose` builds the data-gradient operator
+// (flipped taps, swapped channel roles) before transforming.
+__global__ void conv_prep_wino_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int out_pad,
+                                              int transpose) {
+  const int n_in = transpose ? Cout : Cin;
+  const int n_out = transpose ? Cin : Cout;
+  const size_t total = (size_t)n_in * out_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % out_pad), rowi = (int)(i / out_pad);
+    float g[3][3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float v = 0.f;
+        if (col < n_out) {
+          if (!transpose) v = __ldg(w + ((size_t)col * Cin + rowi) * 9 + ky * 3 + kx);
+          else v = __ldg(w + ((size_t)rowi * Cin + col) * 9 + (2 - ky) * 3 + (2 - kx));
+        }
+        g[ky][kx] = v;
+      }
+    float tmp[4][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      tmp[0][j] = g[0][j];
+      tmp[1][j] = 0.5f * (g[0][j] + g[1][j] + g[2][j]);
+      tmp[2][j] = 0.5f * (g[0][j] - g[1][j] + g[2][j]);
+      tmp[3][j] = g[2][j];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float u0 = tmp[r][0], u1 = 0.5f * (tmp[r][0] + tmp[r][1] + tmp[r][2]), u2 = 0.5f * (tmp[r][0] - tmp[r][1] + tmp[r][2]),
+                  u3 = tmp[r][2];
+      wt[((size_t)(r * 4 + 0) * n_in + rowi) * out_pad + col] = u0;
+      wt[((size_t)(r * 4 + 1) * n_in + rowi) * out_pad + col] = u1;
+      wt[((size_t)(r * 4 + 2) * n_in + rowi) * out_pad + col] = u2;
+      wt[((size_t)(r * 4 + 3) * n_in + rowi) * out_pad + col] = u3;
+    }
+  }
+}
+
 // ---- weight gradient -------------------------------------------------------------------------
 constexpr int WG_GPITCH = CT_H * CT_W + 4;   // 132
 
@@ -553,8 +792,34 @@ static void launch_core(const ConvArgs& args, int cpt, dim3 grid_base, cudaStrea
   else { conv_core_kernel<KS, 1><<<grid, CONV_THREADS, 0, st>>>(args); dd::count_launches(1); }
 }
 
+static bool use_winograd(int ks, int cin, int cout) {
+  static const bool disabled = getenv("DD_NO_WINOGRAD") != nullptr;
+  return !disabled && ks == 3 && cout > 16 && cin >= 8;
+}
+
 static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose,
                     cudaStream_t st) {
+  if (use_winograd(ks, args.Cin, args.Cout)) {
+    args.cout_pad = round_up(args.Cout, WN_CO);
+    const size_t wn = (size_t)args.Cin * args.cout_pad;
+    conv_prep_wino_weights_kernel<<<(int)((wn + 255) / 256 < 592 ? (wn + 255) / 256 : 592), 256, 0, st>>>(
+        w_oihw, wt_buf, Cout_f, Cin_f, args.cout_pad, transpose ? 1 : 0);
+    dd::count_launches(1);
+    args.wt = wt_buf;
+    args.tiles_x = (args.Wo + CT_W - 1) / CT_W;
+    const int tiles_y = (args.Ho + CT_H - 1) / CT_H;
+    static bool configured = false;
+    const size_t smem = WN_SMEM_FLOATS * sizeof(float);
+    if (!configured) {
+      DD_CHECK_CUDA(cudaFuncSetAttribute(conv_wino_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    dim3 grid(args.tiles_x * tiles_y, args.cout_pad / WN_CO, args.B);
+    conv_wino_kernel<<<grid, WN_THREADS, smem, st>>>(args);
+    dd::count_launches(1);
+    DD_CHECK_CUDA(cudaGetLastError());
+    return DD_OK;
+  }
   const int KK = ks * ks;
   const int cpt = cpt_for(args.Cout);
   args.cout_pad = round_up(args.Cout, 8 * cpt);
@@ -579,8 +844,8 @@ static ConvWs conv_ws(const dd_conv_desc* d) {
   ConvWs w;
   const int KK = d->ksize * d->ksize;
   const int Cin = d->C0 + d->C1;
-  const size_t wt_f = (size_t)Cin * KK * round_up(d->Cout, 8 * cpt_for(d->Cout)) * sizeof(float);
-  const size_t wt_d = (size_t)d->Cout * KK * round_up(Cin, 8 * cpt_for(Cin)) * sizeof(float);
+  const size_t wt_f = (size_t)Cin * (KK == 9 ? 16 : KK) * round_up(d->Cout, 32) * sizeof(float);   // covers the Winograd layout
+  const size_t wt_d = (size_t)d->Cout * (KK == 9 ? 16 : KK) * round_up(Cin, 32) * sizeof(float);
   const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
   const size_t Hp = d->H + (reflect ? 2 : 0), Wp = d->W + (reflect ? 2 : 0);
   w.wt = 0;
