@@ -113,6 +113,10 @@ SIGNATURES = {
     "dd_project_bwd": (C.c_int, [FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
     "dd_ssim_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_ssim_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_pose_mean_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_float, FP, FP]),
+    "dd_pose_mean_bwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_float, FP, FP]),
+    "dd_pose_matrix_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, FP, FP]),
+    "dd_pose_matrix_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, FP, FP, FP]),
     "dd_ground_score": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, FP, FP]),
 }
 

@@ -600,3 +600,62 @@ def ground_score(points, w, row0, tol):
     L.check(lib.dd_ground_score(points.data_ptr(), w.data_ptr(), B, H, W, int(row0), K, float(tol), counts.data_ptr(), _stream()),
             "dd_ground_score")
     return counts
+
+
+# ---------------------------------------------------------------------------------------------
+# pose head epilogue (pose_decoder.py:39-44, networks/layers.py:7-82)
+# ---------------------------------------------------------------------------------------------
+
+
+class _PoseMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        lib = L.load()
+        B, Cc, h, w = x.shape
+        out = torch.empty(B, Cc, device=x.device)
+        L.check(lib.dd_pose_mean_fwd(x.data_ptr(), B * Cc, h * w, float(scale), out.data_ptr(), _stream()), "dd_pose_mean_fwd")
+        ctx.dims = (B, Cc, h, w, float(scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        lib = L.load()
+        B, Cc, h, w, scale = ctx.dims
+        gx = torch.empty(B, Cc, h, w, device=go.device)
+        L.check(lib.dd_pose_mean_bwd(go.contiguous().data_ptr(), B * Cc, h * w, scale, gx.data_ptr(), _stream()), "dd_pose_mean_bwd")
+        return gx, None
+
+
+def spatial_mean_scaled(x, scale):
+    """scale * x.mean(3).mean(2) for (B,C,h,w) CUDA tensors."""
+    if not x.is_cuda:
+        raise L.DynamoB200Error("spatial_mean_scaled needs CUDA tensors (no CPU fallback)")
+    return _PoseMeanFn.apply(_prep(x), scale)
+
+
+class _PoseMatrixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, aa, tr, invert):
+        lib = L.load()
+        B = aa.shape[0]
+        T = torch.empty(B, 4, 4, device=aa.device)
+        L.check(lib.dd_pose_matrix_fwd(aa.data_ptr(), tr.data_ptr(), B, int(invert), T.data_ptr(), _stream()), "dd_pose_matrix_fwd")
+        ctx.save_for_backward(aa, tr)
+        ctx.invert = int(invert)
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        lib = L.load()
+        aa, tr = ctx.saved_tensors
+        B = aa.shape[0]
+        gaa, gtr = torch.empty_like(aa), torch.empty_like(tr)
+        L.check(lib.dd_pose_matrix_bwd(aa.data_ptr(), tr.data_ptr(), gT.contiguous().data_ptr(), B, ctx.invert, gaa.data_ptr(),
+                                       gtr.data_ptr(), _stream()), "dd_pose_matrix_bwd")
+        return gaa, gtr, None
+
+
+def pose_matrix(axisangle, translation, invert):
+    """(B,1,3) axis-angle / translation -> (B,4,4) (transformation_from_parameters)."""
+    B = axisangle.shape[0]
+    return _PoseMatrixFn.apply(_prep(axisangle.reshape(B, 3)), _prep(translation.reshape(B, 3)), bool(invert))

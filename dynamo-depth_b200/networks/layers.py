@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from dd_b200.functional import conv2d_fused, resize_bilinear
+from dd_b200.functional import conv2d_fused, pose_matrix, resize_bilinear
 from tools import BackprojectDepth, Project3D, SSIM, compute_smooth_loss, disp_to_depth, depth_to_disp  # noqa: F401
 
 
@@ -43,7 +43,10 @@ def get_translation_matrix(translation_vector):
 
 
 def transformation_from_parameters(axisangle, translation, invert=False):
-    """network (axisangle, translation) -> 4x4; invert=True gives R^T @ Trans(-t) (reference: layers.py:7-24)."""
+    """network (axisangle, translation) -> 4x4; invert=True gives R^T @ Trans(-t) (reference: layers.py:7-24).
+    CUDA tensors go through the fused dd_pose_matrix_* kernels (one launch instead of ~40 ATen ops)."""
+    if axisangle.is_cuda:
+        return pose_matrix(axisangle, translation, invert)
     R = rot_from_axisangle(axisangle)
     t = translation.clone()
     if invert:

@@ -5,7 +5,7 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
-from dd_b200.functional import conv2d_fused
+from dd_b200.functional import conv2d_fused, spatial_mean_scaled
 
 
 class PoseDecoder(nn.Module):
@@ -30,5 +30,5 @@ class PoseDecoder(nn.Module):
         x = conv2d_fused(x, self.pose0.weight, self.pose0.bias, ksize=3, pad="zero", act="relu")
         x = conv2d_fused(x, self.pose1.weight, self.pose1.bias, ksize=3, pad="zero", act="relu")
         x = conv2d_fused(x, self.pose2.weight, self.pose2.bias, ksize=1)
-        out = 0.01 * x.mean(3).mean(2).view(-1, self.num_frames_to_predict_for, 1, 6)
+        out = spatial_mean_scaled(x, 0.01).view(-1, self.num_frames_to_predict_for, 1, 6)
         return out[..., :3], out[..., 3:]

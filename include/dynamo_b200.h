@@ -228,6 +228,18 @@ int dd_ssim_fwd(const float* x, const float* y, int BC, int H, int W, float* out
 int dd_ssim_bwd(const float* x, const float* y, const float* grad_out, int BC, int H, int W, float* grad_x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Pose head epilogue (pose_decoder.py:39-44 and networks/layers.py:7-82)
+ *   dd_pose_mean:   out (B,C) = scale * mean over (h,w) of x (B,C,h,w)           [0.01 * out.mean(3).mean(2)]
+ *   dd_pose_matrix: T (B,4,4) from axis-angle (B,3) and translation (B,3): Rodrigues with axis = v/(|v|+1e-7),
+ *                   invert != 0 -> R^T @ Trans(-t), else Trans(t) @ R  (transformation_from_parameters)
+ * ------------------------------------------------------------------------------------------ */
+int dd_pose_mean_fwd(const float* x, int BC, int hw, float scale, float* out, void* stream);
+int dd_pose_mean_bwd(const float* grad_out, int BC, int hw, float scale, float* grad_x, void* stream);
+int dd_pose_matrix_fwd(const float* axisangle, const float* translation, int B, int invert, float* T, void* stream);
+int dd_pose_matrix_bwd(const float* axisangle, const float* translation, const float* grad_T, int B, int invert,
+                       float* grad_axisangle, float* grad_translation, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RANSAC ground-plane hypothesis scoring (tools.GroundPlane.estimate_ground_plane, tools.py:113-139)
  *   counts[k] = #{ n : | x_n*w[k][0] + z_n*w[k][1] + w[k][2] - y_n | < tol }  over the ground rows
  *   (row >= row0) of image (k % B) -- the reference pairs hypothesis k with image k % B because it tiles
