@@ -548,6 +548,8 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
   for (int q = tid; q < WN_CO * WN_TILES; q += WN_THREADS) {
     const int col = q >> 5, tl = q & 31;
     const int tr = tl >> 3, tc = tl & 7;
+    const int y = ty0 + 2 * tr, x = tx0 + 2 * tc, co = co0 + col;
+    if (co >= a.Cout || y >= a.Ho || x >= a.Wo) continue;
     float m[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -559,11 +561,36 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
       sr[0][j] = m[0][j] + m[1][j] + m[2][j];
       sr[1][j] = m[1][j] - m[2][j] - m[3][j];
     }
-    const int y = ty0 + 2 * tr, x = tx0 + 2 * tc, co = co0 + col;
+    // destination of this channel (single tensor, or the two tensors of a directly written data gradient)
+    float* outp = a.out;
+    size_t plane = ((size_t)b * a.Cout + co);
+    if (a.split > 0) {
+      if (co < a.split) plane = (size_t)b * a.split + co;
+      else outp = a.out1, plane = (size_t)b * (a.Cout - a.split) + (co - a.split);
+      if (outp == nullptr) continue;
+    }
+    const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+    const bool pair = (x + 1 < a.Wo) && ((a.Wo & 1) == 0);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      emit_output(a, b, co, y + i, x, sr[i][0] + sr[i][1] + sr[i][2]);
-      emit_output(a, b, co, y + i, x + 1, sr[i][1] - sr[i][2] - sr[i][3]);
+      if (y + i >= a.Ho) continue;
+      const size_t o = (plane * a.Ho + y + i) * a.Wo + x;
+      float v0 = apply_act(sr[i][0] + sr[i][1] + sr[i][2] + bv, a.act);
+      float v1 = apply_act(sr[i][1] - sr[i][2] - sr[i][3] + bv, a.act);
+      if (pair) {
+        if (a.residual) {
+          const float2 rv = __ldg(reinterpret_cast<const float2*>(a.residual + o));
+          v0 += rv.x, v1 += rv.y;
+        }
+        *reinterpret_cast<float2*>(outp + o) = make_float2(v0, v1);
+      } else {
+        if (a.residual) v0 += __ldg(a.residual + o);
+        outp[o] = v0;
+        if (x + 1 < a.Wo) {
+          if (a.residual) v1 += __ldg(a.residual + o + 1);
+          outp[o + 1] = v1;
+        }
+      }
     }
   }
 }
