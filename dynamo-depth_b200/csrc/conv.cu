@@ -146,11 +146,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
     build_tile_map(a.vin, ty0 + r - HALO + a.oy, tx0 + c - HALO + a.ox, tab0[i], tab1[i]);
   }
 
-  float acc[CPT][8];
+  // accumulators: channel pairs packed for FFMA2 (CPT >= 2), scalar for the single-channel variant
+  constexpr int CP2 = CPT >= 2 ? CPT / 2 : 1;
+  f32x2 acc2[CP2][8];
+  float acc1[8];
 #pragma unroll
-  for (int c = 0; c < CPT; ++c)
+  for (int p = 0; p < 8; ++p) {
+    acc1[p] = 0.f;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) acc[c][p] = 0.f;
+    for (int c = 0; c < CP2; ++c) acc2[c][p] = 0ull;
+  }
 
   // tile-position -> shared-memory offset of this thread's staging slots (k-step invariant)
   auto gather = [&](int ci0, float (&pre)[NPRE]) {
@@ -217,21 +222,28 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
 #pragma unroll
         for (int dx = 0; dx < KS; ++dx) {
           const float* wp = w_s + (ci * KK + dy * KS + dx) * CO_T + cg * CPT;
-          float wv[CPT];
-          if (CPT >= 4) {
+          if (CPT >= 2) {   // (w[c], w[c+1]) * broadcast(iv) + (acc[c], acc[c+1]): one FFMA2 per channel pair and pixel
+            f32x2 wv2[CP2];
+            if (CPT >= 4) {
 #pragma unroll
-            for (int q = 0; q < CPT / 4; ++q) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wp + q * 4);
-              wv[q * 4 + 0] = w4.x, wv[q * 4 + 1] = w4.y, wv[q * 4 + 2] = w4.z, wv[q * 4 + 3] = w4.w;
+              for (int q = 0; q < CPT / 4; ++q) {
+                const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wp + q * 4);
+                wv2[q * 2 + 0] = w4.x, wv2[q * 2 + 1] = w4.y;
+              }
+            } else {
+              wv2[0] = *reinterpret_cast<const f32x2*>(wp);
+            }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const f32x2 ivv = pack2(iv[p + dx], iv[p + dx]);
+#pragma unroll
+              for (int c = 0; c < CP2; ++c) acc2[c][p] = fma2(wv2[c], ivv, acc2[c][p]);
             }
           } else {
+            const float wv = wp[0];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) wv[c] = wp[c];
+            for (int p = 0; p < 8; ++p) acc1[p] = fmaf(wv, iv[p + dx], acc1[p]);
           }
-#pragma unroll
-          for (int c = 0; c < CPT; ++c)
-#pragma unroll
-            for (int p = 0; p < 8; ++p) acc[c][p] = fmaf(wv[c], iv[p + dx], acc[c][p]);
         }
       }
     }
@@ -258,7 +270,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
     float v[8];
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-      v[p] = apply_act(acc[c][p] + bv, a.act);
+      float accv;
+      if (CPT >= 2) {
+        float lo, hi;
+        unpack2(acc2[c >> 1][p], lo, hi);
+        accv = (c & 1) ? hi : lo;
+      } else {
+        accv = acc1[p];
+      }
+      v[p] = apply_act(accv + bv, a.act);
       if (a.residual && xb + p < a.Wo) v[p] += __ldg(a.residual + o + p);
     }
     if (xb + 7 < a.Wo && (a.Wo & 3) == 0) {
@@ -434,11 +454,11 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
     const int r = i / COLS, c = i - r * COLS;
     build_tile_map(a.vin, ty0 + r - 1 + a.oy, tx0 + c - 1 + a.ox, tab0[i], tab1[i]);
   }
-  float acc[8][8];
+  f32x2 acc2[8][4];   // [channel][tile pair]: packed accumulators (FFMA2)
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
-    for (int t = 0; t < 8; ++t) acc[c][t] = 0.f;
+    for (int t = 0; t < 4; ++t) acc2[c][t] = 0ull;
 
   auto gather = [&](int ci0, float (&pre)[NPRE]) {
 #pragma unroll
@@ -523,13 +543,15 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
 #pragma unroll 2
       for (int ci = 0; ci < CI_T; ++ci) {
         const float4 u0 = *reinterpret_cast<const float4*>(up + ci * WN_CO), u1 = *reinterpret_cast<const float4*>(up + ci * WN_CO + 4);
-        const float4 v0 = *reinterpret_cast<const float4*>(vp + ci * WN_VP), v1 = *reinterpret_cast<const float4*>(vp + ci * WN_VP + 4);
+        const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP), v1 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP + 4);
         const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const f32x2 v[4] = {v0.x, v0.y, v1.x, v1.y};
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < 8; ++c) {
+          const f32x2 uu = pack2(u[c], u[c]);
 #pragma unroll
-          for (int tq = 0; tq < 8; ++tq) acc[c][tq] = fmaf(u[c], v[tq], acc[c][tq]);
+          for (int tq = 0; tq < 4; ++tq) acc2[c][tq] = fma2(uu, v[tq], acc2[c][tq]);
+        }
       }
     }
     if (k + 1 < nk) {
@@ -543,7 +565,12 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
-    for (int tq = 0; tq < 8; ++tq) M_s[(p * WN_CO + cg * 8 + c) * WN_MP + tg * 8 + tq] = acc[c][tq];
+    for (int tq = 0; tq < 4; ++tq) {
+      float lo, hi;
+      unpack2(acc2[c][tq], lo, hi);
+      float* mp = M_s + (p * WN_CO + cg * 8 + c) * WN_MP + tg * 8 + 2 * tq;
+      mp[0] = lo, mp[1] = hi;
+    }
   __syncthreads();
   for (int q = tid; q < WN_CO * WN_TILES; q += WN_THREADS) {
     const int col = q >> 5, tl = q & 31;
@@ -637,7 +664,8 @@ __global__ void conv_prep_wino_weights_kernel(const float* __restrict__ w, float
 }
 
 // ---- weight gradient -------------------------------------------------------------------------
-constexpr int WG_GPITCH = CT_H * CT_W + 4;   // 132
+constexpr int WG_GPITCH = CT_H * CT_W + 4;   // 132 (scalar variant: one channel per plane)
+constexpr int WG_PPITCH = 2 * CT_H * CT_W + 4;   // 260 (packed variant: one channel PAIR per plane, pixel-major [pos][2])
 
 struct WgradArgs {
   VirtIn vin;
@@ -657,7 +685,8 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   constexpr int ROWS = CT_H + 2 * HALO, COLS = CT_W + 2 * HALO;
   constexpr int CO_T = 16 * WCO;
   constexpr int NPOS = ROWS * COLS;
-  __shared__ __align__(16) float g_s[CO_T * WG_GPITCH];
+  constexpr bool PACKED = WCO >= 2;   // channel pairs interleaved per pixel so (g[c], g[c+1]) is one 64-bit FFMA2 operand
+  __shared__ __align__(16) float g_s[PACKED ? (CO_T / 2) * WG_PPITCH : CO_T * WG_GPITCH];
   __shared__ __align__(16) float v_s[CI_T * IN_PLANE];
   __shared__ TapEntry tab0[NPOS];
   __shared__ int tab1[NPOS];
@@ -665,7 +694,8 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   const int tid = threadIdx.x;
   // warp = 16 output-channel lanes x 2 input channels: the input-tile loads are (almost) warp-uniform broadcasts and
   // the gradient-tile loads of the 16 lanes fall into distinct banks (channel stride 132 floats); thread owns output
-  // channels co0 + cq + 16*c (c < WCO) and input channel ci0 + ci
+  // channels co0 + cq + 16*c (c < WCO) [scalar] or the pairs co0 + 2*cq + 32*c2 + {0,1} (c2 < WCO/2) [packed] and
+  // input channel ci0 + ci
   const int cq = tid & 15, ci = ((tid >> 5) << 1) + ((tid >> 4) & 1);
   const int co0 = blockIdx.x * CO_T, ci0 = blockIdx.y * CI_T;
   const int n_tiles = a.tiles_x * a.tiles_y;
@@ -674,11 +704,16 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   const int it1 = min(n_items, it0 + a.items_per_split);
   const bool vec_ok = (a.W & 3) == 0;
 
-  float acc[WCO][KK];
+  // accumulators: output-channel pairs packed for FFMA2 (WCO >= 2), scalar otherwise
+  constexpr int WP2 = WCO >= 2 ? WCO / 2 : 1;
+  f32x2 acc2[WP2][KK];
+  float acc1[KK];
 #pragma unroll
-  for (int c = 0; c < WCO; ++c)
+  for (int t = 0; t < KK; ++t) {
+    acc1[t] = 0.f;
 #pragma unroll
-    for (int t = 0; t < KK; ++t) acc[c][t] = 0.f;
+    for (int c = 0; c < WP2; ++c) acc2[c][t] = 0ull;
+  }
 
   for (int it = it0; it < it1; ++it) {
     const int b = it / n_tiles, tile = it - b * n_tiles;
@@ -700,7 +735,12 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
           if (x + 3 < a.W) v.w = __ldg(src + 3);
         }
       }
-      *reinterpret_cast<float4*>(g_s + c * WG_GPITCH + r * CT_W + 4 * q) = v;
+      if (PACKED) {
+        float* gp = g_s + (c >> 1) * WG_PPITCH + (r * CT_W + 4 * q) * 2 + (c & 1);
+        gp[0] = v.x, gp[2] = v.y, gp[4] = v.z, gp[6] = v.w;
+      } else {
+        *reinterpret_cast<float4*>(g_s + c * WG_GPITCH + r * CT_W + 4 * q) = v;
+      }
     }
     for (int i = tid; i < NPOS; i += CONV_THREADS) {
       const int r = i / COLS, cc = i - r * COLS;
@@ -720,10 +760,20 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
 #pragma unroll
       for (int xq = 0; xq < CT_W; xq += 4) {
         float gv[WCO][4];
+        f32x2 gp[WP2][4];   // packed: (g[c][p], g[c+1][p])
+        if (PACKED) {
 #pragma unroll
-        for (int c = 0; c < WCO; ++c) {
-          const float4 g4 = *reinterpret_cast<const float4*>(g_s + (cq + 16 * c) * WG_GPITCH + r * CT_W + xq);
-          gv[c][0] = g4.x, gv[c][1] = g4.y, gv[c][2] = g4.z, gv[c][3] = g4.w;
+          for (int c = 0; c < WP2; ++c) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(g_s + (cq + 16 * c) * WG_PPITCH + (r * CT_W + xq) * 2);
+            const ulonglong2 a01 = src[0], a23 = src[1];
+            gp[c][0] = a01.x, gp[c][1] = a01.y, gp[c][2] = a23.x, gp[c][3] = a23.y;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < WCO; ++c) {
+            const float4 g4 = *reinterpret_cast<const float4*>(g_s + (cq + 16 * c) * WG_GPITCH + r * CT_W + xq);
+            gv[c][0] = g4.x, gv[c][1] = g4.y, gv[c][2] = g4.z, gv[c][3] = g4.w;
+          }
         }
 #pragma unroll
         for (int dy = 0; dy < KS; ++dy) {
@@ -735,12 +785,21 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
             const float2 v2 = *reinterpret_cast<const float2*>(vp + 4);
             vr[4] = v2.x, vr[5] = v2.y;
           }
+          if (PACKED) {
 #pragma unroll
-          for (int dx = 0; dx < KS; ++dx)
+            for (int dx = 0; dx < KS; ++dx)
 #pragma unroll
-            for (int c = 0; c < WCO; ++c)
+              for (int p = 0; p < 4; ++p) {
+                const f32x2 vv = pack2(vr[p + dx], vr[p + dx]);
 #pragma unroll
-              for (int p = 0; p < 4; ++p) acc[c][dy * KS + dx] = fmaf(gv[c][p], vr[p + dx], acc[c][dy * KS + dx]);
+                for (int c = 0; c < WP2; ++c) acc2[c][dy * KS + dx] = fma2(gp[c][p], vv, acc2[c][dy * KS + dx]);
+              }
+          } else {
+#pragma unroll
+            for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+              for (int p = 0; p < 4; ++p) acc1[dy * KS + dx] = fmaf(gv[0][p], vr[p + dx], acc1[dy * KS + dx]);
+          }
         }
       }
     }
@@ -749,10 +808,20 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   if (ci0 + ci < a.Cin) {
 #pragma unroll
     for (int c = 0; c < WCO; ++c) {
-      const int co = co0 + cq + 16 * c;
+      const int co = PACKED ? co0 + 2 * cq + 32 * (c >> 1) + (c & 1) : co0 + cq + 16 * c;
       if (co >= a.Cout) continue;
 #pragma unroll
-      for (int t = 0; t < KK; ++t) atomicAdd(a.gw + ((size_t)co * a.Cin + ci0 + ci) * KK + t, acc[c][t]);
+      for (int t = 0; t < KK; ++t) {
+        float v;
+        if (WCO >= 2) {
+          float lo, hi;
+          unpack2(acc2[c >> 1][t], lo, hi);
+          v = (c & 1) ? hi : lo;
+        } else {
+          v = acc1[t];
+        }
+        atomicAdd(a.gw + ((size_t)co * a.Cin + ci0 + ci) * KK + t, v);
+      }
     }
   }
 }

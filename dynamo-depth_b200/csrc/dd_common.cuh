@@ -34,6 +34,31 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Packed fp32 pairs (sm_100a FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per issue slot, each lane
+// rounded exactly like the scalar instruction).  A pair lives in one 64-bit register (lo = first element).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // Bilinear up-sampling taps of F.interpolate(mode='bilinear', align_corners=False) from an axis of
 // n_in = n_out >> shift samples (ATen UpSample.h area_pixel_compute_source_index): src =
 // (dst+0.5)/2^shift - 0.5 clamped at 0, second tap min(i0+1, n_in-1).  shift==0 is a plain copy.
