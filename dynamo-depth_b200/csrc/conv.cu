@@ -410,7 +410,7 @@ constexpr int WN_CO = 32;
 constexpr int WN_TILES = 32;
 constexpr int WN_VP = 36;    // V_s pitch over tiles
 constexpr int WN_MP = 33;    // M_s pitch over tiles
-constexpr int WN_SMEM_LOOP = 2 * CI_T * IN_PLANE + 16 * CI_T * WN_VP + 2 * 16 * CI_T * WN_CO;
+constexpr int WN_SMEM_LOOP = 2 * CI_T * IN_PLANE + 2 * 16 * CI_T * WN_VP + 2 * 16 * CI_T * WN_CO;
 constexpr int WN_SMEM_EPI = 16 * WN_CO * WN_MP;
 constexpr int WN_SMEM_FLOATS = WN_SMEM_LOOP > WN_SMEM_EPI ? WN_SMEM_LOOP : WN_SMEM_EPI;
 
@@ -428,17 +428,15 @@ __device__ __forceinline__ void emit_output(const ConvArgs& a, int b, int co, in
   outp[o] = v;
 }
 
+// x0 arrives either as is or nearest-up-sampled (one tap per element); bilinear up-sampling is materialised by the host
+// wrapper (materialise_up) before the launch.
 __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int ROWS = CT_H + 2, COLS = CT_W + 2, NPOS = ROWS * COLS;
-  constexpr int N_IN = CI_T * NPOS;
-  constexpr int NPRE = (N_IN + WN_THREADS - 1) / WN_THREADS;
   extern __shared__ __align__(16) float wsm[];
   float* in_s = wsm;                                  // [2][CI_T*IN_PLANE]
-  float* V_s = wsm + 2 * CI_T * IN_PLANE;             // [16][CI_T][WN_VP]
-  float* U_s = V_s + 16 * CI_T * WN_VP;               // [2][16][CI_T][WN_CO], filled by cp.async one step ahead
+  float* V_s = wsm + 2 * CI_T * IN_PLANE;             // [2][16][CI_T][WN_VP], transformed one step ahead
+  float* U_s = V_s + 2 * 16 * CI_T * WN_VP;           // [2][16][CI_T][WN_CO], filled by cp.async one step ahead
   float* M_s = wsm;                                   // epilogue only: [16][WN_CO][WN_MP]
-  __shared__ TapEntry tab0[NPOS];
-  __shared__ int tab1[NPOS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -450,115 +448,141 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
   // transform role: input channel ti, winograd tile tt
   const int ti = tid >> 5, tt = tid & 31, ttr = tt >> 3, ttc = tt & 7;
 
-  for (int i = tid; i < NPOS; i += WN_THREADS) {
-    const int r = i / COLS, c = i - r * COLS;
-    build_tile_map(a.vin, ty0 + r - 1 + a.oy, tx0 + c - 1 + a.ox, tab0[i], tab1[i]);
-  }
+  // Loader role: thread = one position of the 10x18 input tile, all 8 channels of a K-step.  Where that position
+  // reads from (padding, reflection, up-sampling taps) does not depend on the channel or the step, so it is derived
+  // once and kept in registers; per element the loader is then an address add + load.
+  const bool has_pos = tid < NPOS;
+  TapEntry te;
+  int o1;
+  const int lr = tid / COLS, lc = tid - lr * COLS;
+  build_tile_map(a.vin, ty0 + lr - 1 + a.oy, tx0 + lc - 1 + a.ox, te, o1);
+  if (!has_pos) te.o00 = -1, o1 = -1;
+  const int s_off = has_pos ? lr * IN_PITCH + lc : 0;
+  const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win;
+  const float* x0b = a.vin.x0 + (size_t)b * a.vin.C0 * plane0;
+  const float* x1b = a.vin.x1 + (size_t)b * a.vin.C1 * plane1 - (size_t)a.vin.C0 * plane1;   // indexed by the concatenated channel
+  const int C0 = a.vin.C0, Cin = a.Cin;
+
   f32x2 acc2[8][4];   // [channel][tile pair]: packed accumulators (FFMA2)
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc2[c][t] = 0ull;
 
-  auto gather = [&](int ci0, float (&pre)[NPRE]) {
+  auto gather = [&](int ci0, float (&pre)[CI_T]) {
 #pragma unroll
-    for (int j = 0; j < NPRE; ++j) {
-      const int i = tid + j * WN_THREADS;
+    for (int ci = 0; ci < CI_T; ++ci) {
+      const int c = ci0 + ci;   // CTA-uniform
       float v = 0.f;
-      if (i < N_IN) {
-        const int ci = i / NPOS, pos = i - ci * NPOS;
-        if (ci0 + ci < a.Cin) v = map_load(a.vin, b, ci0 + ci, tab0, tab1, pos);
+      if (c < C0) {
+        if (te.o00 >= 0) {
+          const float* pl = x0b + (size_t)c * plane0;
+          v = __ldg(pl + te.o00);
+        }
+      } else if (c < Cin && o1 >= 0) {
+        v = __ldg(x1b + (size_t)c * plane1 + o1);
       }
-      pre[j] = v;
+      pre[ci] = v;
     }
   };
-  auto scatter = [&](int buf, const float (&pre)[NPRE]) {
+  auto scatter = [&](int buf, const float (&pre)[CI_T]) {
+    if (has_pos) {
+      float* dst = in_s + buf * CI_T * IN_PLANE + s_off;
 #pragma unroll
-    for (int j = 0; j < NPRE; ++j) {
-      const int i = tid + j * WN_THREADS;
-      if (i < N_IN) {
-        const int ci = i / NPOS, pos = i - ci * NPOS;
-        const int r = pos / COLS, c = pos - r * COLS;
-        in_s[buf * CI_T * IN_PLANE + ci * IN_PLANE + r * IN_PITCH + c] = pre[j];
-      }
+      for (int ci = 0; ci < CI_T; ++ci) dst[ci * IN_PLANE] = pre[ci];
     }
   };
 
-  auto issue_weights = [&](int ci0, int buf) {   // U_s[buf][p][ci][co] <- wt[p][ci0+ci][co0 + co]
-    for (int i = tid; i < 16 * CI_T * (WN_CO / 4); i += WN_THREADS) {
-      const int q = i & 7, pc = i >> 3;   // pc = p*CI_T + ci
-      const int pp = pc >> 3, ci = pc & 7;
-      const bool ok = ci0 + ci < a.Cin;
-      const float* src = a.wt + ((size_t)pp * a.Cin + (ok ? ci0 + ci : 0)) * a.cout_pad + co0 + q * 4;
-      cp_async16(U_s + buf * 16 * CI_T * WN_CO + i * 4, src, ok);
-    }
+  // U_s[buf][p][ci][co] <- wt[p][ci0+ci][co0 + co]: 16-byte chunk i = tid + 256*j -> (p = tid/64 + 4j, ci = tid/8 % 8, q = tid % 8)
+  const int w_ci = (tid >> 3) & 7;
+  const float* w_src = a.wt + ((size_t)(tid >> 6) * Cin + w_ci) * a.cout_pad + co0 + (tid & 7) * 4;
+  const size_t w_jstride = (size_t)4 * Cin * a.cout_pad;
+  auto issue_weights = [&](int ci0, int buf) {
+    const bool ok = ci0 + w_ci < Cin;
+    const float* src = ok ? w_src + (size_t)ci0 * a.cout_pad : a.wt;
+    float* dst = U_s + buf * 16 * CI_T * WN_CO + tid * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cp_async16(dst + j * 4 * WN_THREADS, ok ? src + j * w_jstride : src, ok);
     cp_async_commit();
   };
 
-  float pre[NPRE];
-  __syncthreads();   // tile map complete
+  // input transform V = B^T d B of (channel ti, tile tt): in_s[ib] -> V_s[vb]
+  auto transform = [&](int ib, int vb) {
+    const float* dp = in_s + ib * CI_T * IN_PLANE + ti * IN_PLANE + (2 * ttr) * IN_PITCH + 2 * ttc;
+    float d[4][4], t[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 lo = *reinterpret_cast<const float2*>(dp + i * IN_PITCH);
+      const float2 hi = *reinterpret_cast<const float2*>(dp + i * IN_PITCH + 2);
+      d[i][0] = lo.x, d[i][1] = lo.y, d[i][2] = hi.x, d[i][3] = hi.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      t[0][j] = d[0][j] - d[2][j];
+      t[1][j] = d[1][j] + d[2][j];
+      t[2][j] = d[2][j] - d[1][j];
+      t[3][j] = d[1][j] - d[3][j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float* vp = V_s + vb * 16 * CI_T * WN_VP + ((i * 4) * CI_T + ti) * WN_VP + tt;
+      vp[0 * CI_T * WN_VP] = t[i][0] - t[i][2];
+      vp[1 * CI_T * WN_VP] = t[i][1] + t[i][2];
+      vp[2 * CI_T * WN_VP] = t[i][2] - t[i][1];
+      vp[3 * CI_T * WN_VP] = t[i][1] - t[i][3];
+    }
+  };
+  // 16 independent [32 co x 8 ci] x [8 ci x 32 tiles] products of one K-step; thread = (frequency, 8 channels, 8 tiles)
+  auto gemm = [&](int buf) {
+    const float* up = U_s + buf * 16 * CI_T * WN_CO + p * CI_T * WN_CO + cg * 8;
+    const float* vp = V_s + buf * 16 * CI_T * WN_VP + p * CI_T * WN_VP + tg * 8;
+#pragma unroll 2
+    for (int ci = 0; ci < CI_T; ++ci) {
+      const float4 u0 = *reinterpret_cast<const float4*>(up + ci * WN_CO), u1 = *reinterpret_cast<const float4*>(up + ci * WN_CO + 4);
+      const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP), v1 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP + 4);
+      const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      const f32x2 v[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const f32x2 uu = pack2(u[c], u[c]);
+#pragma unroll
+        for (int tq = 0; tq < 4; ++tq) acc2[c][tq] = fma2(uu, v[tq], acc2[c][tq]);
+      }
+    }
+  };
+
+  // Software pipeline over K-steps of 8 input channels, ONE barrier per step:
+  //   step k:  cp.async U(k+1) | LDG tile(k+2) -> registers | transform(k+1): in_s -> V_s | GEMM(k) | registers -> in_s(k+2)
+  // The transform and the GEMM of one step are independent; half of the warps run them in the opposite order so that
+  // every SM sub-partition always has a warp on the FMA pipe while another one does the (FMA-free) transform.
+  const int nk = (a.Cin + CI_T - 1) / CI_T;
+  const bool gemm_first = (warp & 4) != 0;
+  float pre[CI_T];
   issue_weights(0, 0);
   gather(0, pre);
   scatter(0, pre);
+  __syncthreads();   // in_s[0] visible
+  if (nk > 1) gather(CI_T, pre);
+  transform(0, 0);
+  if (nk > 1) scatter(1, pre);
   cp_async_wait_all();
-  __syncthreads();
+  __syncthreads();   // V_s[0], U_s[0], in_s[1] visible
 
-  const int nk = (a.Cin + CI_T - 1) / CI_T;
   for (int k = 0; k < nk; ++k) {
     const int buf = k & 1;
-    // input transform V = B^T d B of (channel ti, tile tt)
-    {
-      const float* dp = in_s + buf * CI_T * IN_PLANE + ti * IN_PLANE + (2 * ttr) * IN_PITCH + 2 * ttc;
-      float d[4][4], t[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 lo = *reinterpret_cast<const float2*>(dp + i * IN_PITCH);
-        const float2 hi = *reinterpret_cast<const float2*>(dp + i * IN_PITCH + 2);
-        d[i][0] = lo.x, d[i][1] = lo.y, d[i][2] = hi.x, d[i][3] = hi.y;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        t[0][j] = d[0][j] - d[2][j];
-        t[1][j] = d[1][j] + d[2][j];
-        t[2][j] = d[2][j] - d[1][j];
-        t[3][j] = d[1][j] - d[3][j];
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float* vp = V_s + ((i * 4) * CI_T + ti) * WN_VP + tt;
-        vp[0 * CI_T * WN_VP] = t[i][0] - t[i][2];
-        vp[1 * CI_T * WN_VP] = t[i][1] + t[i][2];
-        vp[2 * CI_T * WN_VP] = t[i][2] - t[i][1];
-        vp[3 * CI_T * WN_VP] = t[i][1] - t[i][3];
-      }
+    const bool next = k + 1 < nk, next2 = k + 2 < nk;
+    if (next) issue_weights((k + 1) * CI_T, buf ^ 1);
+    if (next2) gather((k + 2) * CI_T, pre);   // loads in flight during the arithmetic below
+    if (gemm_first) {
+      gemm(buf);
+      if (next) transform(buf ^ 1, buf ^ 1);
+    } else {
+      if (next) transform(buf ^ 1, buf ^ 1);
+      gemm(buf);
     }
-    __syncthreads();   // V_s of step k visible (U_s[buf] landed before the previous barrier)
-    if (k + 1 < nk) {
-      issue_weights((k + 1) * CI_T, buf ^ 1);
-      gather((k + 1) * CI_T, pre);
-    }
-    {
-      const float* up = U_s + buf * 16 * CI_T * WN_CO + p * CI_T * WN_CO + cg * 8;
-      const float* vp = V_s + p * CI_T * WN_VP + tg * 8;
-#pragma unroll 2
-      for (int ci = 0; ci < CI_T; ++ci) {
-        const float4 u0 = *reinterpret_cast<const float4*>(up + ci * WN_CO), u1 = *reinterpret_cast<const float4*>(up + ci * WN_CO + 4);
-        const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP), v1 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP + 4);
-        const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-        const f32x2 v[4] = {v0.x, v0.y, v1.x, v1.y};
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const f32x2 uu = pack2(u[c], u[c]);
-#pragma unroll
-          for (int tq = 0; tq < 4; ++tq) acc2[c][tq] = fma2(uu, v[tq], acc2[c][tq]);
-        }
-      }
-    }
-    if (k + 1 < nk) {
-      scatter(buf ^ 1, pre);
-      cp_async_wait_all();
-    }
-    __syncthreads();   // GEMM reads of U_s[buf] / V_s done; in_s[buf^1], U_s[buf^1] complete
+    if (next2) scatter(buf, pre);   // in_s[buf] was last read by transform(k) during step k-1
+    cp_async_wait_all();
+    __syncthreads();   // V_s[buf^1], U_s[buf^1], in_s[buf] complete; reads of V_s[buf] / U_s[buf] / in_s[buf^1] done
   }
 
   // epilogue: gather the 16 frequencies of every (channel, tile) through shared memory, Y = A^T m A
@@ -676,33 +700,37 @@ struct WgradArgs {
   float* gw;         // (Cout, Cin, k, k), zero-initialised, accumulated with atomics
 };
 
-// Thread = (group of WCO output channels, one input channel): WCO*k*k accumulators, reduced over the
-// (image, tile) items of this z-slice; CTA = 16 channel groups x 8 input channels.
+// Thread = (WCO output channels, one input channel): WCO*k*k accumulators, reduced over the (image, tile) items of
+// this z-slice; CTA = 8 channel groups x 16 input channels (128 threads).  With WCO = 8 every shared-memory word feeds
+// ~5.8 FMAs (g: 4 pixels x 8 channels, v: 3 x 6 taps per 288 FMAs), which keeps the kernel off the 32 words/clk
+// shared-memory limit that a 4-channel thread tile (4.2 FMAs per word) sits on.
+constexpr int WG_CQ = 8, WG_CI = 16;
+
 template <int KS, int WCO>
 __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
   constexpr int KK = KS * KS;
   constexpr int HALO = KS / 2;
   constexpr int ROWS = CT_H + 2 * HALO, COLS = CT_W + 2 * HALO;
-  constexpr int CO_T = 16 * WCO;
+  constexpr int CO_T = WG_CQ * WCO;
   constexpr int NPOS = ROWS * COLS;
+  constexpr int NSLOT = (NPOS + CONV_THREADS - 1) / CONV_THREADS;   // input-tile positions per thread (2)
   constexpr bool PACKED = WCO >= 2;   // channel pairs interleaved per pixel so (g[c], g[c+1]) is one 64-bit FFMA2 operand
   __shared__ __align__(16) float g_s[PACKED ? (CO_T / 2) * WG_PPITCH : CO_T * WG_GPITCH];
-  __shared__ __align__(16) float v_s[CI_T * IN_PLANE];
-  __shared__ TapEntry tab0[NPOS];
-  __shared__ int tab1[NPOS];
+  __shared__ __align__(16) float v_s[WG_CI * IN_PLANE];
 
   const int tid = threadIdx.x;
-  // warp = 16 output-channel lanes x 2 input channels: the input-tile loads are (almost) warp-uniform broadcasts and
-  // the gradient-tile loads of the 16 lanes fall into distinct banks (channel stride 132 floats); thread owns output
-  // channels co0 + cq + 16*c (c < WCO) [scalar] or the pairs co0 + 2*cq + 32*c2 + {0,1} (c2 < WCO/2) [packed] and
-  // input channel ci0 + ci
-  const int cq = tid & 15, ci = ((tid >> 5) << 1) + ((tid >> 4) & 1);
-  const int co0 = blockIdx.x * CO_T, ci0 = blockIdx.y * CI_T;
+  // warp = 8 channel groups x 4 input channels: gradient-tile loads of the 8 lanes of a quarter-warp are distinct
+  // 16-byte chunks (plane stride 260 / 132 floats), input-tile loads are broadcasts.  Thread owns the output-channel
+  // pairs co0 + 2*(cq + 8*c2) + {0,1} (c2 < WCO/2) [packed] or channel co0 + cq [scalar] and input channel ci0 + ci.
+  const int cq = tid & (WG_CQ - 1), ci = tid >> 3;
+  const int co0 = blockIdx.x * CO_T, ci0 = blockIdx.y * WG_CI;
   const int n_tiles = a.tiles_x * a.tiles_y;
   const int n_items = a.B * n_tiles;
   const int it0 = blockIdx.z * a.items_per_split;
   const int it1 = min(n_items, it0 + a.items_per_split);
   const bool vec_ok = (a.W & 3) == 0;
+  const int C0 = a.vin.C0;
+  const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win;
 
   // accumulators: output-channel pairs packed for FFMA2 (WCO >= 2), scalar otherwise
   constexpr int WP2 = WCO >= 2 ? WCO / 2 : 1;
@@ -718,11 +746,8 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   for (int it = it0; it < it1; ++it) {
     const int b = it / n_tiles, tile = it - b * n_tiles;
     const int ty0 = (tile / a.tiles_x) * CT_H, tx0 = (tile % a.tiles_x) * CT_W;
-    // gradient tile: CO_T channels x 8 rows x 16 pixels, one float4 (4 pixels) per thread and step
-    for (int i = tid; i < CO_T * CT_H * (CT_W / 4); i += CONV_THREADS) {
-      const int c = i >> 5, rem = i & 31;
-      const int r = rem >> 2, q = rem & 3;
-      const int y = ty0 + r, x = tx0 + 4 * q;
+    // gradient tile: CO_T channels x 8 rows x 16 pixels, one float4 (4 pixels) per channel, thread and step
+    auto load_g4 = [&](int c, int y, int x) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (co0 + c < a.Cout && y < a.H) {
         const float* src = a.g + (((size_t)b * a.Cout + co0 + c) * a.H + y) * a.W + x;
@@ -735,45 +760,82 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
           if (x + 3 < a.W) v.w = __ldg(src + 3);
         }
       }
-      if (PACKED) {
-        float* gp = g_s + (c >> 1) * WG_PPITCH + (r * CT_W + 4 * q) * 2 + (c & 1);
-        gp[0] = v.x, gp[2] = v.y, gp[4] = v.z, gp[6] = v.w;
-      } else {
-        *reinterpret_cast<float4*>(g_s + c * WG_GPITCH + r * CT_W + 4 * q) = v;
+      return v;
+    };
+    if (PACKED) {   // two channels per thread, stored pixel-interleaved: (g[c][p], g[c+1][p]) adjacent
+#pragma unroll 2
+      for (int i = tid; i < (CO_T / 2) * CT_H * (CT_W / 4); i += CONV_THREADS) {
+        const int cp = i >> 5, rem = i & 31;
+        const int r = rem >> 2, q = rem & 3;
+        const float4 va = load_g4(2 * cp, ty0 + r, tx0 + 4 * q), vb = load_g4(2 * cp + 1, ty0 + r, tx0 + 4 * q);
+        float4* dst = reinterpret_cast<float4*>(g_s + cp * WG_PPITCH + (r * CT_W + 4 * q) * 2);
+        dst[0] = make_float4(va.x, vb.x, va.y, vb.y);
+        dst[1] = make_float4(va.z, vb.z, va.w, vb.w);
+      }
+    } else {
+      for (int i = tid; i < CO_T * CT_H * (CT_W / 4); i += CONV_THREADS) {
+        const int c = i >> 5, rem = i & 31;
+        const int r = rem >> 2, q = rem & 3;
+        *reinterpret_cast<float4*>(g_s + c * WG_GPITCH + r * CT_W + 4 * q) = load_g4(c, ty0 + r, tx0 + 4 * q);
       }
     }
-    for (int i = tid; i < NPOS; i += CONV_THREADS) {
-      const int r = i / COLS, cc = i - r * COLS;
-      build_tile_map(a.vin, ty0 + r - HALO, tx0 + cc - HALO, tab0[i], tab1[i]);
-    }
-    __syncthreads();
-    for (int i = tid; i < CI_T * NPOS; i += CONV_THREADS) {
-      const int c = i / NPOS, pos = i - c * NPOS;
-      const int r = pos / COLS, cc = pos - r * COLS;
-      float v = 0.f;
-      if (ci0 + c < a.Cin) v = map_load(a.vin, b, ci0 + c, tab0, tab1, pos);
-      v_s[c * IN_PLANE + r * IN_PITCH + cc] = v;
+    // input tile: thread = fixed tile position(s), all 16 channels; the position's source (padding, reflection,
+    // up-sampling tap) is channel independent and derived once per item
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      const int pos = tid + sl * CONV_THREADS;
+      if (pos < NPOS) {
+        const int r = pos / COLS, cc = pos - r * COLS;
+        TapEntry te;
+        int o1;
+        build_tile_map(a.vin, ty0 + r - HALO, tx0 + cc - HALO, te, o1);
+        float* dst = v_s + r * IN_PITCH + cc;
+        const float* x0b = a.vin.x0 + ((size_t)b * C0 + ci0) * plane0;
+        const float* x1b = a.vin.x1 + ((size_t)b * a.vin.C1 + (ci0 - C0)) * plane1;
+#pragma unroll
+        for (int ch = 0; ch < WG_CI; ch += 8) {
+          float pre[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = ci0 + ch + k;   // CTA-uniform
+            float v = 0.f;
+            if (c < C0) {
+              if (te.o00 >= 0) {
+                const float* pl = x0b + (size_t)(ch + k) * plane0;
+                if (a.vin.up0 != DD_UP_BILINEAR2) {
+                  v = __ldg(pl + te.o00);
+                } else {
+                  const float v00 = __ldg(pl + te.o00), v01 = __ldg(pl + te.o01), v10 = __ldg(pl + te.o10), v11 = __ldg(pl + te.o11);
+                  v = (1.f - te.ly) * ((1.f - te.lx) * v00 + te.lx * v01) + te.ly * ((1.f - te.lx) * v10 + te.lx * v11);
+                }
+              }
+            } else if (c < a.Cin && o1 >= 0) {
+              v = __ldg(x1b + (size_t)(ch + k) * plane1 + o1);
+            }
+            pre[k] = v;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[(ch + k) * IN_PLANE] = pre[k];
+        }
+      }
     }
     __syncthreads();
 #pragma unroll 1
     for (int r = 0; r < CT_H; ++r) {
 #pragma unroll
       for (int xq = 0; xq < CT_W; xq += 4) {
-        float gv[WCO][4];
+        float gv[4];
         f32x2 gp[WP2][4];   // packed: (g[c][p], g[c+1][p])
         if (PACKED) {
 #pragma unroll
           for (int c = 0; c < WP2; ++c) {
-            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(g_s + (cq + 16 * c) * WG_PPITCH + (r * CT_W + xq) * 2);
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(g_s + (cq + WG_CQ * c) * WG_PPITCH + (r * CT_W + xq) * 2);
             const ulonglong2 a01 = src[0], a23 = src[1];
             gp[c][0] = a01.x, gp[c][1] = a01.y, gp[c][2] = a23.x, gp[c][3] = a23.y;
           }
         } else {
-#pragma unroll
-          for (int c = 0; c < WCO; ++c) {
-            const float4 g4 = *reinterpret_cast<const float4*>(g_s + (cq + 16 * c) * WG_GPITCH + r * CT_W + xq);
-            gv[c][0] = g4.x, gv[c][1] = g4.y, gv[c][2] = g4.z, gv[c][3] = g4.w;
-          }
+          const float4 g4 = *reinterpret_cast<const float4*>(g_s + cq * WG_GPITCH + r * CT_W + xq);
+          gv[0] = g4.x, gv[1] = g4.y, gv[2] = g4.z, gv[3] = g4.w;
         }
 #pragma unroll
         for (int dy = 0; dy < KS; ++dy) {
@@ -798,7 +860,7 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
 #pragma unroll
             for (int dx = 0; dx < KS; ++dx)
 #pragma unroll
-              for (int p = 0; p < 4; ++p) acc1[dy * KS + dx] = fmaf(gv[0][p], vr[p + dx], acc1[dy * KS + dx]);
+              for (int p = 0; p < 4; ++p) acc1[dy * KS + dx] = fmaf(gv[p], vr[p + dx], acc1[dy * KS + dx]);
           }
         }
       }
@@ -808,12 +870,12 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   if (ci0 + ci < a.Cin) {
 #pragma unroll
     for (int c = 0; c < WCO; ++c) {
-      const int co = PACKED ? co0 + 2 * cq + 32 * (c >> 1) + (c & 1) : co0 + cq + 16 * c;
+      const int co = PACKED ? co0 + 2 * (cq + WG_CQ * (c >> 1)) + (c & 1) : co0 + cq;
       if (co >= a.Cout) continue;
 #pragma unroll
       for (int t = 0; t < KK; ++t) {
         float v;
-        if (WCO >= 2) {
+        if (PACKED) {
           float lo, hi;
           unpack2(acc2[c >> 1][t], lo, hi);
           v = (c & 1) ? hi : lo;
@@ -849,6 +911,32 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __rest
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+
+static int device_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+      sms = 148;
+  }
+  return sms;
+}
+
+template <int KS>
+static int wgrad_occupancy(int wco) {
+  static int occ[4] = {0, 0, 0, 0};
+  const int slot = wco == 8 ? 3 : (wco == 4 ? 2 : (wco == 2 ? 1 : 0));
+  if (occ[slot] == 0) {
+    int n = 0;
+    cudaError_t e;
+    if (wco == 8) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_wgrad_kernel<KS, 8>, CONV_THREADS, 0);
+    else if (wco == 4) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_wgrad_kernel<KS, 4>, CONV_THREADS, 0);
+    else if (wco == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_wgrad_kernel<KS, 2>, CONV_THREADS, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_wgrad_kernel<KS, 1>, CONV_THREADS, 0);
+    occ[slot] = (e == cudaSuccess && n > 0) ? n : 4;
+  }
+  return occ[slot];
+}
 
 static inline int cpt_for(int cout) { return cout > 32 ? 8 : (cout > 16 ? 4 : (cout > 8 ? 2 : 1)); }
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -910,6 +998,7 @@ static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, 
       DD_CHECK_CUDA(cudaFuncSetAttribute(conv_wino_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;
     }
+    DD_REQUIRE(args.vin.up0 != DD_UP_BILINEAR2, "conv_wino_kernel: bilinear up-sampling must be materialised first");
     dim3 grid(args.tiles_x * tiles_y, args.cout_pad / WN_CO, args.B);
     conv_wino_kernel<<<grid, WN_THREADS, smem, st>>>(args);
     dd::count_launches(1);
@@ -933,8 +1022,27 @@ static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, 
 }
 
 struct ConvWs {
-  size_t wt, gconv, wtd, gpad, total;
+  size_t wt, up, gconv, wtd, gpad, total;
+  size_t fwd_bytes;   // what the forward pass needs (prepared weights + materialised up-sampling)
 };
+
+__global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int BC, int hi, int wi, int ho, int wo,
+                                  int sigmoid);
+
+// Bilinear x2 up-sampling of x0 (depth_decoder.py:104) is materialised once per call into the workspace (a few tens of
+// MB, written and read once at HBM speed) so that the convolution loaders stay one tap per element; returns the
+// virtual-input description the kernels should use.
+static VirtIn materialise_up(const dd_conv_desc* d, void* workspace, const ConvWs& ws, cudaStream_t st) {
+  VirtIn v = make_vin(d);
+  if (d->up0 != DD_UP_BILINEAR2) return v;
+  float* up = reinterpret_cast<float*>((char*)workspace + ws.up);
+  const size_t n = (size_t)d->B * d->C0 * d->H * d->W;
+  resize_fwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(d->x0, up, d->B * d->C0, d->H / 2, d->W / 2,
+                                                                                          d->H, d->W, 0);
+  dd::count_launches(1);
+  v.x0 = up, v.H0 = d->H, v.W0 = d->W, v.up0 = DD_UP_NONE;
+  return v;
+}
 
 static ConvWs conv_ws(const dd_conv_desc* d) {
   ConvWs w;
@@ -945,7 +1053,9 @@ static ConvWs conv_ws(const dd_conv_desc* d) {
   const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
   const size_t Hp = d->H + (reflect ? 2 : 0), Wp = d->W + (reflect ? 2 : 0);
   w.wt = 0;
-  w.gconv = align256(wt_f);
+  w.up = align256(wt_f);
+  w.gconv = w.up + (d->up0 == DD_UP_BILINEAR2 ? align256((size_t)d->B * d->C0 * d->H * d->W * sizeof(float)) : 0);
+  w.fwd_bytes = w.gconv;
   w.wtd = w.gconv + align256((size_t)d->B * d->Cout * d->H * d->W * sizeof(float));
   w.gpad = w.wtd + align256(wt_d);
   w.total = w.gpad + align256((size_t)d->B * Cin * Hp * Wp * sizeof(float));
@@ -957,13 +1067,13 @@ int conv_fwd_impl(const dd_conv_desc* d, float* out, void* workspace, size_t byt
   if (rc != DD_OK) return rc;
   DD_REQUIRE(out != nullptr, "dd_conv_fwd: out is NULL");
   const ConvWs ws = conv_ws(d);
-  if (!workspace || bytes < ws.gconv) {
-    set_error("dd_conv_fwd: workspace too small (%zu < %zu)", bytes, ws.gconv);
+  if (!workspace || bytes < ws.fwd_bytes) {
+    set_error("dd_conv_fwd: workspace too small (%zu < %zu)", bytes, ws.fwd_bytes);
     return DD_ERR_WORKSPACE;
   }
   ConvArgs args;
   memset(&args, 0, sizeof(args));
-  args.vin = make_vin(d);
+  args.vin = materialise_up(d, workspace, ws, st);
   args.B = d->B, args.Ho = d->H, args.Wo = d->W, args.oy = 0, args.ox = 0;
   args.Cin = d->C0 + d->C1, args.Cout = d->Cout;
   args.bias = d->bias, args.residual = d->residual, args.act = d->act, args.out = out;
@@ -1002,20 +1112,23 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));
     WgradArgs wa;
     memset(&wa, 0, sizeof(wa));
-    wa.vin = make_vin(d);
+    wa.vin = materialise_up(d, workspace, ws, st);
     wa.g = g, wa.B = d->B, wa.H = d->H, wa.W = d->W, wa.Cin = Cin, wa.Cout = d->Cout, wa.gw = grad_weight;
     wa.tiles_x = (d->W + CT_W - 1) / CT_W, wa.tiles_y = (d->H + CT_H - 1) / CT_H;
     const int n_items = d->B * wa.tiles_x * wa.tiles_y;
-    const int wco = d->Cout > 32 ? 4 : (d->Cout > 16 ? 2 : 1);
-    const int gx = (d->Cout + 16 * wco - 1) / (16 * wco), gy = (Cin + CI_T - 1) / CI_T;
-    int splits = (148 * 6 + gx * gy - 1) / (gx * gy);   // ~6 CTAs per SM in flight
+    const int wco = d->Cout > 32 ? 8 : (d->Cout > 16 ? 4 : (d->Cout > 8 ? 2 : 1));
+    const int gx = (d->Cout + WG_CQ * wco - 1) / (WG_CQ * wco), gy = (Cin + WG_CI - 1) / WG_CI;
+    // exactly one wave of resident CTAs (a partial second wave would leave most SMs idle for its whole duration)
+    const int resident = device_sms() * (d->ksize == 3 ? wgrad_occupancy<3>(wco) : wgrad_occupancy<1>(wco));
+    int splits = resident / (gx * gy);
     splits = splits < 1 ? 1 : (splits > n_items ? n_items : splits);
     wa.items_per_split = (n_items + splits - 1) / splits;
     splits = (n_items + wa.items_per_split - 1) / wa.items_per_split;
     dim3 grid(gx, gy, splits);
 #define DD_WGRAD(KSZ)                                                                    \
   do {                                                                                   \
-    if (wco == 4) conv_wgrad_kernel<KSZ, 4><<<grid, CONV_THREADS, 0, st>>>(wa);          \
+    if (wco == 8) conv_wgrad_kernel<KSZ, 8><<<grid, CONV_THREADS, 0, st>>>(wa);          \
+    else if (wco == 4) conv_wgrad_kernel<KSZ, 4><<<grid, CONV_THREADS, 0, st>>>(wa);     \
     else if (wco == 2) conv_wgrad_kernel<KSZ, 2><<<grid, CONV_THREADS, 0, st>>>(wa);     \
     else conv_wgrad_kernel<KSZ, 1><<<grid, CONV_THREADS, 0, st>>>(wa);                   \
     dd::count_launches(1);                                                               \
