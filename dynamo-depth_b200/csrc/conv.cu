@@ -458,10 +458,14 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
   build_tile_map(a.vin, ty0 + lr - 1 + a.oy, tx0 + lc - 1 + a.ox, te, o1);
   if (!has_pos) te.o00 = -1, o1 = -1;
   const int s_off = has_pos ? lr * IN_PITCH + lc : 0;
-  const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win;
-  const float* x0b = a.vin.x0 + (size_t)b * a.vin.C0 * plane0;
-  const float* x1b = a.vin.x1 + (size_t)b * a.vin.C1 * plane1 - (size_t)a.vin.C0 * plane1;   // indexed by the concatenated channel
   const int C0 = a.vin.C0, Cin = a.Cin;
+  const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win;
+  const bool ok0 = te.o00 >= 0, ok1 = o1 >= 0;
+  // running sources of this thread's position: channel c of the concatenated input lives at src0 + c*plane0 (c < C0)
+  // or src1 + c*plane1 (c >= C0; src1 is pre-shifted by -C0 planes); both advance by 8 planes per K-step
+  const float* src0 = a.vin.x0 + (size_t)b * C0 * plane0 + (ok0 ? te.o00 : 0);
+  const float* src1 = a.vin.x1 ? a.vin.x1 + (size_t)b * a.vin.C1 * plane1 + (ok1 ? o1 : 0) : a.vin.x0;
+  if (a.vin.x1) src1 -= (size_t)C0 * plane1;
 
   f32x2 acc2[8][4];   // [channel][tile pair]: packed accumulators (FFMA2)
 #pragma unroll
@@ -469,20 +473,19 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc2[c][t] = 0ull;
 
+  // gathers the 8 channels of the K-step starting at channel ci0 (steps are visited in order: the running pointers
+  // advance by one plane per channel)
   auto gather = [&](int ci0, float (&pre)[CI_T]) {
 #pragma unroll
     for (int ci = 0; ci < CI_T; ++ci) {
       const int c = ci0 + ci;   // CTA-uniform
+      const bool in0 = c < C0;
+      const float* ptr = in0 ? src0 : src1;
+      const bool ok = in0 ? ok0 : (ok1 && c < Cin);
       float v = 0.f;
-      if (c < C0) {
-        if (te.o00 >= 0) {
-          const float* pl = x0b + (size_t)c * plane0;
-          v = __ldg(pl + te.o00);
-        }
-      } else if (c < Cin && o1 >= 0) {
-        v = __ldg(x1b + (size_t)c * plane1 + o1);
-      }
+      if (ok) v = __ldg(ptr);
       pre[ci] = v;
+      src0 += plane0, src1 += plane1;
     }
   };
   auto scatter = [&](int buf, const float (&pre)[CI_T]) {
