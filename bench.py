@@ -227,6 +227,19 @@ def run_ours(args):
     ms_e2e, _, _ = timed(pinned, args.steps, True)
     h2d = sum(v.numel() * v.element_size() for v in {id(v): v for v in pinned[0].values()}.values())
 
+    # opt-in variant (not the headline): Lite-Mono linear layers on the TF32 tensor cores (--encoder_tf32_linear)
+    variants = None
+    if not args.no_variants:
+        from networks.depth_encoder import EncoderLinear
+        EncoderLinear.tf32 = True
+        timed(resident, 2, False)
+        ms_v, _, _ = timed(resident, max(3, args.steps // 2), False)
+        EncoderLinear.tf32 = False
+        v_steps = max(3, args.steps // 2)
+        variants = {"encoder_linear_tf32": {"value": world * BATCH * v_steps / (ms_v / 1000), "unit": UNIT, "ms_per_step": ms_v / v_steps,
+                                            "steps": v_steps, "note": "options --encoder_tf32_linear: the Lite-Mono encoder's nn.Linear "
+                                            "contractions in TF32 (scoped; everything else as in `value`); default keeps torch's fp32 matmul"}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -271,12 +284,12 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args.phase), "global_batch": world * BATCH, "parallelism": f"dp{world}",
                        "l2": "per-step working set (>= 141 MB of colour frames plus GBs of activations) exceeds the 126 MB L2; no flush needed",
-                       "encoders": "PyTorch/cuDNN (TF32 convolutions, torch default); decoders + loss path: hand-written fp32 kernels",
+                       "encoders": "PyTorch/cuDNN (TF32 convolutions = torch default, fp32 linear layers, channels_last ResNets); decoders + loss path: hand-written fp32 kernels",
                        "d_ground": "reference RANSAC prior kept on (host-driven torch ops, SURVEY 8f-1)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clock_info}
+            "gpu_launches": int(launches), "clocks": clock_info, "variants": variants}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -290,6 +303,7 @@ def main():
     ap.add_argument("--phase", default="fine_tune", choices=["disp_init", "motion_init", "mask_init", "fine_tune"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the opt-in variant measurement (encoder linear layers in TF32)")
     ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around one step (for ncu), no JSON line")
     args = ap.parse_args()
     if args.impl == "reference":

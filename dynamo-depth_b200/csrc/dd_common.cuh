@@ -59,6 +59,16 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   return d;
 }
 
+// 1/x for normal, finite x: MUFU.RCP + one Newton step (two FMAs).  The result is the correctly rounded reciprocal for
+// all but a vanishing fraction of inputs (and within 1 ulp for those) without __frcp_rn's range check and slow path;
+// the quantities inverted here (depth scale, projective z + 1e-7, SSIM denominators >= C1*C2) are never denormal or inf.
+__device__ __forceinline__ float rcp_nr(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  const float e = fmaf(-x, r, 1.f);
+  return fmaf(r, e, r);
+}
+
 // Bilinear up-sampling taps of F.interpolate(mode='bilinear', align_corners=False) from an axis of
 // n_in = n_out >> shift samples (ATen UpSample.h area_pixel_compute_source_index): src =
 // (dst+0.5)/2^shift - 0.5 clamped at 0, second tap min(i0+1, n_in-1).  shift==0 is a plain copy.

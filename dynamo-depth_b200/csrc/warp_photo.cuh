@@ -67,7 +67,7 @@ __device__ __forceinline__ Proj project_K(const float* K, const Vec4& X) {
   p.c1 = K[4] * X.x + K[5] * X.y + K[6] * X.z + K[7] * X.w;
   p.z = (K[8] * X.x + K[9] * X.y + K[10] * X.z + K[11] * X.w) + 1e-7f;
   // one correctly rounded reciprocal + two multiplies instead of two divisions (<= 1.5 ulp from c/z)
-  p.iz = __frcp_rn(p.z);
+  p.iz = rcp_nr(p.z);
   p.px = p.c0 * p.iz;
   p.py = p.c1 * p.iz;
   return p;

@@ -107,7 +107,7 @@ __device__ __forceinline__ float ssim_raw(float mu_x, float sig_x, float sig_xy,
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
   const float n = (2.f * mu_x * mu_y + C1) * (2.f * sig_xy + C2);
   const float dn = (mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2);
-  return (1.f - n * __frcp_rn(dn)) * 0.5f;
+  return (1.f - n * rcp_nr(dn)) * 0.5f;
 }
 
 // weight with which full-resolution sample `dst` reads low-resolution sample `i` under bilinear
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
         const Taps ty = up_taps(r, shift, h), tx = up_taps(c, shift, w);
         PixelGeom pg;
         const float du = bilerp(disp, w, ty, tx);
-        pg.depth = __frcp_rn(a.min_disp + a.disp_range * du);
+        pg.depth = rcp_nr(a.min_disp + a.disp_range * du);
         const float u = (float)c, v = (float)r;
         pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
                   cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
             const float A1 = 2.f * mx * my + C1, A2 = 2.f * sxy + C2;
             const float B1 = mx * mx + my * my + C1, B2 = sx + sy + C2;
             const float n = A1 * A2, dn = B1 * B2;
-            const float inv_d = __frcp_rn(dn);
+            const float inv_d = rcp_nr(dn);
             const float dS_dmu = (2.f * my * (A2 - A1) * dn - n * 2.f * mx * (B2 - B1)) * inv_d * inv_d;
             const float dS_dxx = -n * B1 * inv_d * inv_d;
             const float dS_dxy = 2.f * A1 * inv_d;
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
       PixelGeom pg;
       {
         const float du = bilerp(disp, w, ty, tx);
-        pg.depth = __frcp_rn(a.min_disp + a.disp_range * du);
+        pg.depth = rcp_nr(a.min_disp + a.disp_range * du);
         const float u = (float)c, v = (float)r;
         pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
                   cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};

@@ -17,7 +17,7 @@
 namespace dd {
 
 constexpr int HALO1 = TILE + 2;   // 34
-constexpr int PITCH1 = 36;
+constexpr int PITCH1 = 35;   // odd pitch: conflict-free rows; 3 CTAs x (dynamic + static + 1 KB) must stay <= 196 KB (carve-out step)
 constexpr int PLANE1 = HALO1 * PITCH1;
 
 struct FwdArgs {
@@ -34,6 +34,23 @@ __device__ __forceinline__ float* smem_Y(float* s) { return s; }
 __device__ __forceinline__ float* smem_X(float* s, int f) { return s + 3 * PLANE1 * (1 + f); }
 __device__ __forceinline__ float* smem_lo(float* s) { return s + 9 * PLANE1; }
 constexpr int LO_PLANE = (TILE / 2) * (TILE / 2);   // 256 low-res pixels per tile at level 1 (the largest staged level)
+// levels > 0: the low-resolution disp / flow / mask texels every halo pixel of the tile interpolates from, staged once
+// per level with cp.async ((TILE >> s) + 2)^2 texels per plane; 9 planes: disp | flow f0 xyz | flow f1 xyz | mask f0 | mask f1
+constexpr int PATCH_MAXW = TILE / 2 + 2;              // 18 (level 1)
+constexpr int PATCH_PLANE = PATCH_MAXW * PATCH_MAXW;  // 324
+__device__ __forceinline__ float* smem_patch(float* s, int mode) { return s + 9 * PLANE1 + (mode >= 1 ? 2 * 5 * LO_PLANE : 0); }
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::); }
+
+// bilinear up-sampling from a staged patch (same expression as bilerp(): identical rounding)
+__device__ __forceinline__ float patch_bilerp(const float* __restrict__ pl, int pw, int y0, int y1, int x0, int x1, float ly, float lx) {
+  const float v00 = pl[y0 * pw + x0], v01 = pl[y0 * pw + x1], v10 = pl[y1 * pw + x0], v11 = pl[y1 * pw + x1];
+  return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
 
 struct SsimOut {
   float L[2][4];   // per frame, per row of the thread's 4-row run
@@ -88,7 +105,7 @@ __device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const f
           const float sig_xy = (axy[f] + hxy[f]) * inv9 - mu_x * mu_y;
           const float n = (2.f * mu_x * mu_y + C1) * (2.f * sig_xy + C2);
           const float dn = (mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2);
-          const float s = fminf(fmaxf((1.f - n * __frcp_rn(dn)) * 0.5f, 0.f), 1.f);
+          const float s = fminf(fmaxf((1.f - n * rcp_nr(dn)) * 0.5f, 0.f), 1.f);
           ssim_acc[f][k] += s;
           l1_acc[f][k] += fabsf(yc_prev - xc_prev[f]);
         }
@@ -153,6 +170,33 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
     float* lo = smem_lo(smem);
     for (int i = tid; i < 2 * 5 * LO_PLANE; i += WP_THREADS) lo[i] = 0.f;
   }
+  // issues the cp.async copies of level si's low-resolution patch (no-op for full-resolution levels)
+  auto stage_patch = [&](int si) {
+    const int shift = d.scale[si];
+    if (shift == 0) return;
+    const int h = H >> shift, w = W >> shift, pw = (TILE >> shift) + 2;
+    const int br = (r0 >> shift) - 1, bc = (c0 >> shift) - 1;
+    const size_t p_lo = (size_t)h * w;
+    float* patch = smem_patch(smem, MODE);
+    // thread = patch texel(s); every plane of that texel shares the (clamped) source offset
+    for (int slot = tid; slot < pw * pw; slot += WP_THREADS) {
+      const int pr = slot / pw, pc = slot - pr * pw;
+      const int off = min(max(br + pr, 0), h - 1) * w + min(max(bc + pc, 0), w - 1);
+      float* dst = patch + slot;
+      cp_async4(dst, d.disp[si] + (size_t)b * p_lo + off);
+      if (MODE >= 1) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo + off;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) cp_async4(dst + (1 + 3 * f + k) * PATCH_PLANE, fl + k * p_lo);
+          if (MODE == 2) cp_async4(dst + (1 + 3 * F + f) * PATCH_PLANE, d.mask[si][f] + (size_t)b * p_lo + off);
+        }
+      }
+    }
+  };
+  stage_patch(0);
+
   const float l1_w = 1.f - d.ssim_weight;
   SsimOut ident;
   if (automask) {   // identity reprojection losses (Trainer.py:327-333), level independent
@@ -166,6 +210,11 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
     const size_t p_lo = (size_t)h * w;
     const float* disp = d.disp[si] + (size_t)b * p_lo;
 
+    const float* patch = smem_patch(smem, MODE);
+    const int pw = (TILE >> shift) + 2, pbr = (r0 >> shift) - 1, pbc = (c0 >> shift) - 1;
+    cp_async_commit_wait();
+    __syncthreads();   // this level's low-resolution patch is in shared memory
+
     float s_cc[2] = {0.f, 0.f}, s_mag[2] = {0.f, 0.f};
     // ---- stage A: warp every halo pixel of both frames ---------------------------------------
     for (int i = tid; i < HALO1 * HALO1; i += WP_THREADS) {
@@ -173,10 +222,13 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
       const bool interior = (hr >= 1) && (hr <= TILE) && (hc >= 1) && (hc <= TILE);
       const int r = reflect1(r0 - 1 + hr, H), c = reflect1(c0 - 1 + hc, W);
       const Taps ty = up_taps(r, shift, h), tx = up_taps(c, shift, w);
+      // patch-relative tap indices (levels > 0)
+      const int py0 = ty.i0 - pbr, py1 = ty.i1 - pbr, px0 = tx.i0 - pbc, px1 = tx.i1 - pbc;
       PixelGeom pg;
       {
-        const float du = bilerp(disp, w, ty, tx);                      // Trainer.py:225
-        pg.depth = __frcp_rn(a.min_disp + a.disp_range * du);            // tools.py:291-298
+        const float du = shift == 0 ? __ldg(disp + (size_t)r * W + c)
+                                    : patch_bilerp(patch, pw, py0, py1, px0, px1, ty.l, tx.l);   // Trainer.py:225
+        pg.depth = rcp_nr(a.min_disp + a.disp_range * du);            // tools.py:291-298
         const float u = (float)c, v = (float)r;
         pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
                   cam.iK[6] * u + cam.iK[7] * v + cam.iK[8]};            // tools.py:193
@@ -189,11 +241,18 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
         Vec3 cf = {0.f, 0.f, 0.f};
         float m = 1.f;
         if (MODE >= 1) {
-          const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo;
           const float tsv = cam.ts[f];
-          cf = {bilerp(fl, w, ty, tx) * tsv, bilerp(fl + p_lo, w, ty, tx) * tsv,
-                bilerp(fl + 2 * p_lo, w, ty, tx) * tsv};               // Trainer.py:251
-          if (MODE == 2) m = bilerp(d.mask[si][f] + (size_t)b * p_lo, w, ty, tx);   // Trainer.py:242
+          if (shift == 0) {
+            const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo + (size_t)r * W + c;
+            cf = {__ldg(fl) * tsv, __ldg(fl + p_lo) * tsv, __ldg(fl + 2 * p_lo) * tsv};               // Trainer.py:251
+            if (MODE == 2) m = __ldg(d.mask[si][f] + (size_t)b * p_lo + (size_t)r * W + c);            // Trainer.py:242
+          } else {
+            const float* fp = patch + (1 + 3 * f) * PATCH_PLANE;
+            cf = {patch_bilerp(fp, pw, py0, py1, px0, px1, ty.l, tx.l) * tsv,
+                  patch_bilerp(fp + PATCH_PLANE, pw, py0, py1, px0, px1, ty.l, tx.l) * tsv,
+                  patch_bilerp(fp + 2 * PATCH_PLANE, pw, py0, py1, px0, px1, ty.l, tx.l) * tsv};
+            if (MODE == 2) m = patch_bilerp(patch + (1 + 3 * F + f) * PATCH_PLANE, pw, py0, py1, px0, px1, ty.l, tx.l);
+          }
         }
         FrameGeom g;
         frame_geometry<MODE>(g, pg, &cam, f, cf, m, H, W, interior);
@@ -247,6 +306,7 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
       }
     }
     __syncthreads();
+    if (si + 1 < d.num_scales) stage_patch(si + 1);   // next level's patch streams in under stages B and C
 
     // ---- stage B: SSIM + L1 + min selection ---------------------------------------------------
     float s_photo = 0.f, s_ident = 0.f;
@@ -381,6 +441,7 @@ int warp_photo_fwd_impl(const dd_warp_desc* desc, const dd_warp_aux* aux, float*
   const int mode = (desc->flags & DD_FLAG_CMPFLOW) ? ((desc->flags & DD_FLAG_MOTMASK) ? 2 : 1) : 0;
   size_t smem_bytes = 9 * PLANE1 * sizeof(float);
   if (mode >= 1) smem_bytes += 2 * 5 * LO_PLANE * sizeof(float);
+  smem_bytes += (mode == 0 ? 1 : (mode == 1 ? 1 + 3 * desc->num_frames : 1 + 4 * desc->num_frames)) * PATCH_PLANE * sizeof(float);
   const int F = desc->num_frames;
   if (mode == 0 && F == 2) rc = launch_fwd<0, 2>(args, grid, smem_bytes, st);
   else if (mode == 1 && F == 2) rc = launch_fwd<1, 2>(args, grid, smem_bytes, st);

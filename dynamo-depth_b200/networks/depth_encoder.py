@@ -34,6 +34,47 @@ class DropPath(nn.Module):
         return x * mask
 
 
+class _LinearTF32(torch.autograd.Function):
+    """F.linear with the three GEMMs (forward, input gradient, weight gradient) on the TF32 tensor cores; the global
+    matmul precision flag is only raised around these calls, so nothing else (e.g. the RANSAC least squares) changes."""
+
+    @staticmethod
+    def _tf32(fn):
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return fn()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return _LinearTF32._tf32(lambda: F.linear(x, weight, bias))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
+        gx = _LinearTF32._tf32(lambda: g2 @ weight).reshape(x.shape) if ctx.needs_input_grad[0] else None
+        gw = _LinearTF32._tf32(lambda: g2.t() @ x2) if ctx.needs_input_grad[1] else None
+        gb = g2.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
+class EncoderLinear(nn.Linear):
+    """nn.Linear of the encoder (same parameters / state_dict keys).  `tf32 = True` (opt-in, options
+    --encoder_tf32_linear) runs its contractions on the tensor cores in TF32 like every cuDNN convolution of the
+    reference already does under torch defaults; the default stays fp32 (torch's default for matmul)."""
+    tf32 = False
+
+    def forward(self, x):
+        if EncoderLinear.tf32 and x.is_cuda:
+            return _LinearTF32.apply(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
+
+
 class LayerNorm(nn.Module):
     """channels_last (default) or channels_first layer norm with learnable affine."""
 
@@ -85,9 +126,9 @@ class XCA(nn.Module):
         super().__init__()
         self.num_heads = num_heads
         self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
-        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.qkv = EncoderLinear(dim, dim * 3, bias=qkv_bias)
         self.attn_drop = nn.Dropout(attn_drop)
-        self.proj = nn.Linear(dim, dim)
+        self.proj = EncoderLinear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
 
     def forward(self, x):
@@ -147,9 +188,9 @@ class DilatedConv(nn.Module):
         self.ddwconv = CDilated(dim, dim, kSize=k, stride=stride, groups=dim, d=dilation)
         self.bn1 = nn.BatchNorm2d(dim)
         self.norm = LayerNorm(dim, eps=1e-6)   # present in the state dict, unused in forward (as in the reference)
-        self.pwconv1 = nn.Linear(dim, expan_ratio * dim)
+        self.pwconv1 = EncoderLinear(dim, expan_ratio * dim)
         self.act = nn.GELU()
-        self.pwconv2 = nn.Linear(expan_ratio * dim, dim)
+        self.pwconv2 = EncoderLinear(expan_ratio * dim, dim)
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones(dim)) if layer_scale_init_value > 0 else None
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
@@ -171,9 +212,9 @@ class LGFI(nn.Module):
         self.gamma_xca = nn.Parameter(layer_scale_init_value * torch.ones(dim)) if layer_scale_init_value > 0 else None
         self.xca = XCA(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
         self.norm = LayerNorm(dim, eps=1e-6)
-        self.pwconv1 = nn.Linear(dim, expan_ratio * dim)
+        self.pwconv1 = EncoderLinear(dim, expan_ratio * dim)
         self.act = nn.GELU()
-        self.pwconv2 = nn.Linear(expan_ratio * dim, dim)
+        self.pwconv2 = EncoderLinear(expan_ratio * dim, dim)
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones(dim)) if layer_scale_init_value > 0 else None
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 

@@ -43,6 +43,9 @@ class Model(nn.Module):
         # opt-in: skip the depth passes on frames -1/+1, which no loss term consumes.
         # Off by default because it changes BatchNorm running statistics / the DropPath RNG stream.
         self.skip_unused_depth = bool(getattr(options, "skip_unused_depth", False))
+        # opt-in: the Lite-Mono encoder's linear layers on the TF32 tensor cores (default fp32, torch's matmul default)
+        from . import depth_encoder as _de
+        _de.EncoderLinear.tf32 = bool(getattr(options, "encoder_tf32_linear", False))
 
     def forward(self, inputs):
         outputs = {}

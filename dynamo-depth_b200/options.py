@@ -69,6 +69,9 @@ _ARGS = [
     (("--eval_img_bound",), dict(nargs="+", type=int, default=None)),
     (("--eval_img_ext",), dict(type=str, choices=[".png", ".jpg"], default=None)),
     (("--eval_img_type",), dict(type=str, choices=["original", "downsample"], default=None)),
+    # B200 build only (not in the reference; defaults keep the reference's behaviour)
+    (("--skip_unused_depth",), dict(action="store_true")),     # no depth passes on frames -1/+1 (no loss term reads them)
+    (("--encoder_tf32_linear",), dict(action="store_true")),   # Lite-Mono linear layers on the TF32 tensor cores
 ]
 
 # values filled in when the corresponding option is left at None (options.py:274-301)
