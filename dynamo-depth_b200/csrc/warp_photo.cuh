@@ -108,6 +108,20 @@ __device__ __forceinline__ float sample_plane(const float* __restrict__ img, int
   return nw * (ft.wx0 * ft.wy0) + ne * (ft.wx1 * ft.wy0) + sw * (ft.wx0 * ft.wy1) + se * (ft.wx1 * ft.wy1);
 }
 
+// Low-resolution operands (disp_s, flow_s, mask_s at levels > 0) are staged per tile in shared memory with 4-byte
+// cp.async copies: ((tile >> s) + 2)^2 texels per plane cover every tap the tile's pixels interpolate from.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::); }
+
+// bilinear up-sampling from a staged patch (same expression as bilerp(): identical rounding)
+__device__ __forceinline__ float patch_bilerp(const float* __restrict__ pl, int pw, int y0, int y1, int x0, int x1, float ly, float lx) {
+  const float v00 = pl[y0 * pw + x0], v01 = pl[y0 * pw + x1], v10 = pl[y1 * pw + x0], v11 = pl[y1 * pw + x1];
+  return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
+
 // Everything one pixel of one (scale, frame) needs.  MODE: 0 rigid, 1 CmpFlow, 2 CmpFlow+MotMask
 // (Trainer.py:248-278).
 struct PixelGeom {

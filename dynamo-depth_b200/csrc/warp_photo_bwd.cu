@@ -22,10 +22,12 @@ namespace dd {
 constexpr int BT_W = 32, BT_H = 16;           // backward tile
 constexpr int H2_W = BT_W + 4, H2_H = BT_H + 4;   // 36 x 20 (halo 2)
 constexpr int H1_W = BT_W + 2, H1_H = BT_H + 2;   // 34 x 18 (halo 1)
-constexpr int PITCH2 = 40;
-constexpr int PLANE2 = H2_H * PITCH2;          // 800
-constexpr int CPITCH = 36;
-constexpr int CPLANE = H1_H * CPITCH;          // 648
+// odd pitches: conflict-free rows, and two CTAs (dynamic + static + 1 KB each) stay inside the 164 KB carve-out step
+constexpr int PITCH2 = 37;
+constexpr int PLANE2 = H2_H * PITCH2;          // 740
+constexpr int CPITCH = 35;
+constexpr int CPLANE = H1_H * CPITCH;          // 630
+constexpr int BP_PLANE = (BT_H / 2 + 2) * (BT_W / 2 + 2);   // 180: low-resolution patch plane (level 1 is the largest)
 constexpr int GPLANE = BT_W * BT_H;            // 512
 
 struct BwdArgs {
@@ -44,7 +46,8 @@ constexpr int SM_X = 3 * PLANE2;
 constexpr int SM_LID = 9 * PLANE2;
 constexpr int SM_COEF = SM_LID + 2 * CPLANE;
 constexpr int SM_GT = SM_COEF + 10 * CPLANE;
-constexpr int SM_TOTAL = SM_GT + 9 * GPLANE;
+constexpr int SM_PATCH = SM_GT + 9 * GPLANE;   // [9][BP_PLANE]: disp | flow f0 xyz | flow f1 xyz | mask f0 | mask f1
+constexpr int SM_TOTAL = SM_PATCH + 9 * BP_PLANE;
 
 // Per-position SSIM statistics of all three channels and both frames from 3x3 windows, produced by a
 // register ring that marches down one column of the halo-2 tiles (3 horizontal taps per row from
@@ -199,6 +202,28 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
     const float g_photo = __ldg(a.grad_sums + si * DD_NSUM + DD_SUM_PHOTO);
     const float g_coef = (-0.5f * (ssim_w / 3.f) * g_photo) / 9.f;   // d loss / d S per window tap
 
+    // low-resolution patch of this level (consumed by stage C; the copies land under stages A and B)
+    const float* patch = smem + SM_PATCH;
+    const int ppw = (BT_W >> shift) + 2, pph = (BT_H >> shift) + 2;
+    const int pbr = (r0 >> shift) - 1, pbc = (c0 >> shift) - 1;
+    if (shift != 0) {
+      for (int slot = tid; slot < ppw * pph; slot += WP_THREADS) {
+        const int pr = slot / ppw, pc = slot - pr * ppw;
+        const int off = min(max(pbr + pr, 0), h - 1) * w + min(max(pbc + pc, 0), w - 1);
+        float* dst = smem + SM_PATCH + slot;
+        cp_async4(dst, disp + off);
+        if (MODE >= 1) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo + off;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) cp_async4(dst + (1 + 3 * f + k) * BP_PLANE, fl + k * p_lo);
+            if (MODE == 2) cp_async4(dst + (7 + f) * BP_PLANE, d.mask[si][f] + (size_t)b * p_lo + off);
+          }
+        }
+      }
+    }
+
     // ---- stage A: warped frames over the 2-pixel halo --------------------------------------------
     if (SAVED) {
       for (int i = tid; i < H2_W * H2_H; i += WP_THREADS) {
@@ -323,6 +348,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
         }
       });
     }
+    cp_async_commit_wait();
     __syncthreads();
 
     // ---- stage C: per-pixel chain ----------------------------------------------------------------
@@ -408,9 +434,10 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
       for (int f = 0; f < 2; ++f) gcf_up[f][0] = gcf_up[f][1] = gcf_up[f][2] = gm_up[f] = 0.f;
 
       const Taps ty = up_taps(r, shift, h), tx = up_taps(c, shift, w);
+      const int py0 = ty.i0 - pbr, py1 = ty.i1 - pbr, px0 = tx.i0 - pbc, px1 = tx.i1 - pbc;   // patch-relative taps
       PixelGeom pg;
       {
-        const float du = bilerp(disp, w, ty, tx);
+        const float du = shift == 0 ? __ldg(disp + (size_t)r * W + c) : patch_bilerp(patch, ppw, py0, py1, px0, px1, ty.l, tx.l);
         pg.depth = rcp_nr(a.min_disp + a.disp_range * du);
         const float u = (float)c, v = (float)r;
         pg.ray = {cam.iK[0] * u + cam.iK[1] * v + cam.iK[2], cam.iK[3] * u + cam.iK[4] * v + cam.iK[5],
@@ -426,10 +453,18 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
         Vec3 cf = {0.f, 0.f, 0.f};
         float m = 1.f;
         if (MODE >= 1) {
-          const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo;
           const float tsv = cam.ts[f];
-          cf = {bilerp(fl, w, ty, tx) * tsv, bilerp(fl + p_lo, w, ty, tx) * tsv, bilerp(fl + 2 * p_lo, w, ty, tx) * tsv};
-          if (MODE == 2) m = bilerp(d.mask[si][f] + (size_t)b * p_lo, w, ty, tx);
+          if (shift == 0) {
+            const float* fl = d.flow[si][f] + (size_t)b * 3 * p_lo + (size_t)r * W + c;
+            cf = {__ldg(fl) * tsv, __ldg(fl + p_lo) * tsv, __ldg(fl + 2 * p_lo) * tsv};
+            if (MODE == 2) m = __ldg(d.mask[si][f] + (size_t)b * p_lo + (size_t)r * W + c);
+          } else {
+            const float* fp = patch + (1 + 3 * f) * BP_PLANE;
+            cf = {patch_bilerp(fp, ppw, py0, py1, px0, px1, ty.l, tx.l) * tsv,
+                  patch_bilerp(fp + BP_PLANE, ppw, py0, py1, px0, px1, ty.l, tx.l) * tsv,
+                  patch_bilerp(fp + 2 * BP_PLANE, ppw, py0, py1, px0, px1, ty.l, tx.l) * tsv};
+            if (MODE == 2) m = patch_bilerp(patch + (7 + f) * BP_PLANE, ppw, py0, py1, px0, px1, ty.l, tx.l);
+          }
         }
         FrameGeom g;
         frame_geometry<MODE>(g, pg, &cam, f, cf, m, H, W, false);
@@ -540,51 +575,64 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
       const int narr = MODE == 0 ? 1 : (MODE == 1 ? 7 : 9);
       const int win = 2 << shift, half = 1 << (shift - 1);
       float* V = COEF;   // [narr][tl_h][32] -- the coefficient maps are dead after stage C
-      // pass 1: V[a][li][c] = sum over the tile rows that read low-res row gi of wy * GT[a][row][c]
-      for (int t = tid; t < narr * tl_h * BT_W; t += WP_THREADS) {
-        const int cx = t & (BT_W - 1);
-        const int al = t >> 5;
-        const int arr = al / tl_h, li = al - arr * tl_h;
+      // pass 1: V[a][li][c] = sum over the tile rows that read low-res row gi of wy * GT[a][row][c];
+      // thread = (li, c): the row weights are shared by all `narr` gradient planes
+      for (int t = tid; t < tl_h * BT_W; t += WP_THREADS) {
+        const int cx = t & (BT_W - 1), li = t >> 5;
         const int gi = (r0 >> shift) - 1 + li;
-        float acc = 0.f;
+        float acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = 0.f;
         if (gi >= 0 && gi < h) {
           const int rs = (gi << shift) - half;
-          for (int e = 0; e < win; ++e) {
+          const int e0 = max(0, r0 - rs), e1 = min(win, r0 + BT_H - rs);
+          for (int e = e0; e < e1; ++e) {
             const int rr = rs + e;
-            if (rr < r0 || rr >= r0 + BT_H) continue;
-            acc += tri_weight(rr, shift, h, gi) * GT[arr * GPLANE + (rr - r0) * BT_W + cx];
+            const float wy = tri_weight(rr, shift, h, gi);
+            const float* gp = GT + (rr - r0) * BT_W + cx;
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+              if (k < narr) acc[k] += wy * gp[k * GPLANE];
           }
         }
-        V[t] = acc;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+          if (k < narr) V[(k * tl_h + li) * BT_W + cx] = acc[k];
       }
       __syncthreads();
-      // pass 2: out[a][li][lj] = sum over the tile columns that read low-res column gj of wx * V[a][li][col]
-      for (int t = tid; t < narr * tl_h * tl_w; t += WP_THREADS) {
-        const int lj = t % tl_w;
-        const int al = t / tl_w;
-        const int arr = al / tl_h, li = al - arr * tl_h;
+      // pass 2: out[a][li][lj] = sum over the tile columns that read low-res column gj of wx * V[a][li][col];
+      // thread = (li, lj)
+      for (int t = tid; t < tl_h * tl_w; t += WP_THREADS) {
+        const int li = t / tl_w, lj = t - li * tl_w;
         const int gi = (r0 >> shift) - 1 + li, gj = (c0 >> shift) - 1 + lj;
         if (gi < 0 || gi >= h || gj < 0 || gj >= w) continue;
         const int cs = (gj << shift) - half;
-        float acc = 0.f;
-        for (int e = 0; e < win; ++e) {
+        const int e0 = max(0, c0 - cs), e1 = min(win, c0 + BT_W - cs);
+        float acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+        for (int e = e0; e < e1; ++e) {
           const int cc = cs + e;
-          if (cc < c0 || cc >= c0 + BT_W) continue;
-          acc += tri_weight(cc, shift, w, gj) * V[al * BT_W + (cc - c0)];
+          const float wx = tri_weight(cc, shift, w, gj);
+          const float* vp = V + li * BT_W + (cc - c0);
+#pragma unroll
+          for (int k = 0; k < 9; ++k)
+            if (k < narr) acc[k] += wx * vp[k * tl_h * BT_W];
         }
-        if (acc == 0.f) continue;
         const size_t ol = (size_t)gi * w + gj;
-        float* dst = nullptr;
-        if (arr == 0) {
-          dst = want_disp ? a.g.disp[si] + (size_t)b * p_lo + ol : nullptr;
-        } else if (arr < 7) {
-          const int f = (arr - 1) / 3, ch = (arr - 1) - f * 3;
-          dst = (f < F && a.g.flow[si][f]) ? a.g.flow[si][f] + ((size_t)b * 3 + ch) * p_lo + ol : nullptr;
-        } else {
-          const int f = arr - 7;
-          dst = (f < F && a.g.mask[si][f]) ? a.g.mask[si][f] + (size_t)b * p_lo + ol : nullptr;
+        if (want_disp && acc[0] != 0.f) atomicAdd(a.g.disp[si] + (size_t)b * p_lo + ol, acc[0]);
+        if (MODE >= 1) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            if (a.g.flow[si][f]) {
+              float* gf = a.g.flow[si][f] + (size_t)b * 3 * p_lo + ol;
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch)
+                if (acc[1 + f * 3 + ch] != 0.f) atomicAdd(gf + ch * p_lo, acc[1 + f * 3 + ch]);
+            }
+            if (MODE == 2 && a.g.mask[si][f] && acc[7 + f] != 0.f) atomicAdd(a.g.mask[si][f] + (size_t)b * p_lo + ol, acc[7 + f]);
+          }
         }
-        if (dst) atomicAdd(dst, acc);
       }
       __syncthreads();
     }

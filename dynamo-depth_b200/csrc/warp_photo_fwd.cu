@@ -40,17 +40,6 @@ constexpr int PATCH_MAXW = TILE / 2 + 2;              // 18 (level 1)
 constexpr int PATCH_PLANE = PATCH_MAXW * PATCH_MAXW;  // 324
 __device__ __forceinline__ float* smem_patch(float* s, int mode) { return s + 9 * PLANE1 + (mode >= 1 ? 2 * 5 * LO_PLANE : 0); }
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::); }
-
-// bilinear up-sampling from a staged patch (same expression as bilerp(): identical rounding)
-__device__ __forceinline__ float patch_bilerp(const float* __restrict__ pl, int pw, int y0, int y1, int x0, int x1, float ly, float lx) {
-  const float v00 = pl[y0 * pw + x0], v01 = pl[y0 * pw + x1], v10 = pl[y1 * pw + x0], v11 = pl[y1 * pw + x1];
-  return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-}
 
 struct SsimOut {
   float L[2][4];   // per frame, per row of the thread's 4-row run
