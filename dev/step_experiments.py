@@ -15,7 +15,6 @@ import bench  # noqa: E402
 def run(tag, steps, channels_last=False, tf32=False, phase="fine_tune"):
     from Trainer import Trainer
     from dd_b200 import synthetic
-    torch.backends.cuda.matmul.allow_tf32 = tf32
     torch.backends.cudnn.benchmark = True
     opt = bench.make_opt(bench.BATCH, 0)
     torch.manual_seed(1234)
@@ -24,9 +23,12 @@ def run(tag, steps, channels_last=False, tf32=False, phase="fine_tune"):
     tr.bool_automask = phase == "disp_init"
     tr.num_steps_per_epoch, tr.step = 100, 100
     tr.set_train()
-    if channels_last:
-        tr.model.pose_enc.to(memory_format=torch.channels_last)
-        tr.model.motion_enc.to(memory_format=torch.channels_last)
+    if channels_last:   # Lite-Mono encoder in NHWC as well (the ResNet encoders already are by default)
+        tr.model.depth_enc.to(memory_format=torch.channels_last)
+        orig = tr.model.depth_enc.forward
+        tr.model.depth_enc.forward = lambda x: orig(x.contiguous(memory_format=torch.channels_last))
+    from networks.depth_encoder import EncoderLinear
+    EncoderLinear.tf32 = tf32
     batches = synthetic.SyntheticTriplets(opt, steps=1, device=tr.device, seed=1234, distinct=2).batches
     for i in range(3):
         tr.train_step(dict(batches[i % 2]))
@@ -49,6 +51,5 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=8)
     a = ap.parse_args()
     run("baseline fine_tune", a.steps)
-    run("channels_last resnet encoders", a.steps, channels_last=True)
-    run("tf32 matmul (lite-mono linear layers)", a.steps, tf32=True)
-    run("baseline disp_init", a.steps, phase="disp_init")
+    run("lite-mono encoder channels_last", a.steps, channels_last=True)
+    run("scoped tf32 lite-mono linear layers", a.steps, tf32=True)

@@ -126,12 +126,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
   constexpr int NPOS = ROWS * COLS;
   constexpr int CO_T = 8 * CPT;
   constexpr int NV = 8 + KS - 1;
-  constexpr int N_IN = CI_T * NPOS;
-  constexpr int NPRE = (N_IN + CONV_THREADS - 1) / CONV_THREADS;
+  constexpr int NSLOT = (NPOS + CONV_THREADS - 1) / CONV_THREADS;   // input-tile positions per thread (2 for 3x3, 1 for 1x1)
   __shared__ __align__(16) float in_s[2][CI_T * IN_PLANE];
   __shared__ __align__(16) float w_s[CI_T * KK * CO_T];
-  __shared__ TapEntry tab0[NPOS];
-  __shared__ int tab1[NPOS];
 
   const int tid = threadIdx.x;
   const int pg = tid & 15, cg = tid >> 4;
@@ -141,9 +138,26 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
   const int co0 = blockIdx.y * CO_T;
   const int b = blockIdx.z;
 
-  for (int i = tid; i < NPOS; i += CONV_THREADS) {
-    const int r = i / COLS, c = i - r * COLS;
-    build_tile_map(a.vin, ty0 + r - HALO + a.oy, tx0 + c - HALO + a.ox, tab0[i], tab1[i]);
+  // Loader role: thread = fixed position(s) of the input tile, all 8 channels of a K-step.  The position's source
+  // (padding, reflection, nearest up-sampling) is channel and step independent: derived once, kept in registers as
+  // running pointers that advance one plane per channel (bilinear up-sampling is materialised by the host wrapper).
+  const int C0 = a.vin.C0, Cin = a.Cin;
+  const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win;
+  const float* src0[NSLOT];
+  const float* src1[NSLOT];
+  bool ok0[NSLOT], ok1[NSLOT];
+  int s_off[NSLOT];
+#pragma unroll
+  for (int sl = 0; sl < NSLOT; ++sl) {
+    const int pos = tid + sl * CONV_THREADS;
+    const int r = pos / COLS, c = pos - r * COLS;
+    TapEntry te;
+    int o1;
+    build_tile_map(a.vin, ty0 + r - HALO + a.oy, tx0 + c - HALO + a.ox, te, o1);
+    ok0[sl] = pos < NPOS && te.o00 >= 0, ok1[sl] = pos < NPOS && o1 >= 0 && a.vin.x1 != nullptr;
+    s_off[sl] = pos < NPOS ? r * IN_PITCH + c : -1;
+    src0[sl] = a.vin.x0 + (size_t)b * C0 * plane0 + (ok0[sl] ? te.o00 : 0);
+    src1[sl] = ok1[sl] ? a.vin.x1 + ((ptrdiff_t)b * a.vin.C1 - C0) * (ptrdiff_t)plane1 + o1 : a.vin.x0;
   }
 
   // accumulators: channel pairs packed for FFMA2 (CPT >= 2), scalar for the single-channel variant
@@ -157,29 +171,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
     for (int c = 0; c < CP2; ++c) acc2[c][p] = 0ull;
   }
 
-  // tile-position -> shared-memory offset of this thread's staging slots (k-step invariant)
-  auto gather = [&](int ci0, float (&pre)[NPRE]) {
+  // K-steps are visited in order: every call advances the running pointers by 8 planes
+  auto gather = [&](int ci0, float (&pre)[NSLOT][CI_T]) {
 #pragma unroll
-    for (int j = 0; j < NPRE; ++j) {
-      const int i = tid + j * CONV_THREADS;
-      float v = 0.f;
-      if (i < N_IN) {
-        const int ci = i / NPOS, pos = i - ci * NPOS;
-        if (ci0 + ci < a.Cin) v = map_load(a.vin, b, ci0 + ci, tab0, tab1, pos);
+    for (int ci = 0; ci < CI_T; ++ci) {
+      const int c = ci0 + ci;   // CTA-uniform
+      const bool in0 = c < C0;
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const float* ptr = in0 ? src0[sl] : src1[sl];
+        const bool ok = in0 ? ok0[sl] : (ok1[sl] && c < Cin);
+        float v = 0.f;
+        if (ok) v = __ldg(ptr);
+        pre[sl][ci] = v;
+        src0[sl] += plane0, src1[sl] += plane1;
       }
-      pre[j] = v;
     }
   };
-  auto scatter = [&](int buf, const float (&pre)[NPRE]) {
+  auto scatter = [&](int buf, const float (&pre)[NSLOT][CI_T]) {
 #pragma unroll
-    for (int j = 0; j < NPRE; ++j) {
-      const int i = tid + j * CONV_THREADS;
-      if (i < N_IN) {
-        const int ci = i / NPOS, pos = i - ci * NPOS;
-        const int r = pos / COLS, c = pos - r * COLS;
-        in_s[buf][ci * IN_PLANE + r * IN_PITCH + c] = pre[j];
+    for (int sl = 0; sl < NSLOT; ++sl)
+      if (s_off[sl] >= 0) {
+#pragma unroll
+        for (int ci = 0; ci < CI_T; ++ci) in_s[buf][ci * IN_PLANE + s_off[sl]] = pre[sl][ci];
       }
-    }
   };
   auto stage_weights = [&](int ci0) {
     constexpr int PER = CO_T / 4;
@@ -193,8 +208,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
     }
   };
 
-  float pre[NPRE];
-  __syncthreads();   // tile map complete
+  float pre[NSLOT][CI_T];
   gather(0, pre);
   scatter(0, pre);
 
@@ -464,8 +478,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
   // running sources of this thread's position: channel c of the concatenated input lives at src0 + c*plane0 (c < C0)
   // or src1 + c*plane1 (c >= C0; src1 is pre-shifted by -C0 planes); both advance by 8 planes per K-step
   const float* src0 = a.vin.x0 + (size_t)b * C0 * plane0 + (ok0 ? te.o00 : 0);
-  const float* src1 = a.vin.x1 ? a.vin.x1 + (size_t)b * a.vin.C1 * plane1 + (ok1 ? o1 : 0) : a.vin.x0;
-  if (a.vin.x1) src1 -= (size_t)C0 * plane1;
+  const float* src1 = a.vin.x1 ? a.vin.x1 + ((ptrdiff_t)b * a.vin.C1 - C0) * (ptrdiff_t)plane1 + (ok1 ? o1 : 0) : a.vin.x0;
 
   f32x2 acc2[8][4];   // [channel][tile pair]: packed accumulators (FFMA2)
 #pragma unroll
