@@ -349,7 +349,12 @@ class Trainer:
         """('color',0,s) for s>0: chained bicubic-antialias x1/2, clamped (reference: Trainer.py:729-734)."""
         for s in self.opt.scales:
             if s != 0 and ("color", 0, s) not in inputs:
-                inputs[("color", 0, s)] = torch.clamp(self.resize[s](inputs[("color", 0, s - 1)]), 0, 1)
+                prev = inputs[("color", 0, s - 1)]
+                if prev.is_cuda and prev.shape[-2] % 2 == 0 and prev.shape[-1] % 2 == 0 and \
+                        tuple(prev.shape[-2:]) == (2 * (self.H >> s), 2 * (self.W >> s)):
+                    inputs[("color", 0, s)] = Fn.pyramid_half(prev)       # hand-written kernel (dd_pyramid_half_fwd)
+                else:                                                     # host-side tensors (data-loader workers)
+                    inputs[("color", 0, s)] = torch.clamp(self.resize[s](prev), 0, 1)
 
     def save_opt(self):
         folder = join_dir(self.log_path, "models")

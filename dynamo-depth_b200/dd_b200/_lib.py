@@ -107,6 +107,7 @@ SIGNATURES = {
     "dd_conv_bwd": (C.c_int, [C.POINTER(ConvDesc), FP, FP, FP, FP, FP, FP, FP, C.c_size_t, FP]),
     "dd_resize_bilinear_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_resize_bilinear_bwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_pyramid_half_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_backproject_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_backproject_bwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_project_fwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP]),

@@ -494,6 +494,18 @@ def resize_bilinear(x, size, sigmoid=False):
 # ---------------------------------------------------------------------------------------------
 
 
+def pyramid_half(x):
+    """clamp(bicubic-antialias x1/2 of x, 0, 1): one link of the input colour pyramid (Trainer.py:80, 729-734).
+    x: (B, C, H, W) CUDA fp32 with even H, W; input data, no gradient."""
+    if not x.is_cuda:
+        raise L.DynamoB200Error("pyramid_half needs CUDA tensors (no CPU fallback)")
+    x = _prep(x.detach())
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, Cc, H // 2, W // 2, device=x.device)
+    L.check(L.load().dd_pyramid_half_fwd(x.data_ptr(), B * Cc, H, W, out.data_ptr(), _stream()), "dd_pyramid_half_fwd")
+    return out
+
+
 class _BackprojectFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, depth, inv_K):

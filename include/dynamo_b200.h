@@ -209,6 +209,14 @@ int dd_resize_bilinear_bwd(const float* grad_out, const float* out, int BC, int 
                            int sigmoid, float* grad_x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input colour pyramid: out (BC, H/2, W/2) = clamp(bicubic-antialias x1/2 of x (BC, H, W), 0, 1) —
+ * one link of the chain Trainer.apply_img_resize builds (Trainer.py:729-734 with the torchvision
+ * Resize(BICUBIC, antialias=True) of Trainer.py:80, i.e. ATen _upsample_bicubic2d_aa).  H, W even.  No gradient
+ * (the pyramid is input data: it only feeds the edge weights of compute_smooth_loss, tools.py:311-326).
+ * ------------------------------------------------------------------------------------------ */
+int dd_pyramid_half_fwd(const float* x, int BC, int H, int W, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stand-alone geometry / photometric layers (the module surface eval scripts and user code call:
  * trainer.backproject_depth[s](depth, inv_K), trainer.project_3d[s](points, K, T), SSIM()(x, y)).
  * The training step itself goes through dd_warp_photo_* and never materialises these tensors.
