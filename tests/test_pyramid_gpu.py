@@ -17,7 +17,7 @@ def _reference_chain(x, levels):
     return out
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 192, 640), (3, 3, 64, 96), (1, 3, 32, 34), (1, 1, 6, 8), (2, 3, 2, 2)])
+@pytest.mark.parametrize("shape", [(2, 3, 192, 640), (3, 3, 64, 96), (1, 3, 32, 36), (1, 1, 6, 8), (2, 3, 2, 2)])
 def test_pyramid_half_matches_torchvision(shape):
     from dd_b200 import functional as Fn
 
