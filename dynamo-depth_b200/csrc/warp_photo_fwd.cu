@@ -28,10 +28,12 @@ struct FwdArgs {
   int has_aux;
 };
 
-// shared memory carve-up (floats): Y[3][34][36] | X[2][3][34][36] | lo[2][5][16][16] (flow modes: low-resolution
+// shared memory carve-up (floats): Y[3][34][35] | XI[3][34][35][2] | lo[2][5][16][16] (flow modes: low-resolution
 // accumulators of the 2^s-block centre averages, filled with shared-memory atomics)
 __device__ __forceinline__ float* smem_Y(float* s) { return s; }
-__device__ __forceinline__ float* smem_X(float* s, int f) { return s + 3 * PLANE1 * (1 + f); }
+// warped (or identity) source tiles, frame-interleaved: element (ch, pos, f) at XI[(ch*PLANE1 + pos)*2 + f], so that the
+// two frames of a pixel are one 64-bit word = one FFMA2 operand of the SSIM statistics
+__device__ __forceinline__ float* smem_XI(float* s) { return s + 3 * PLANE1; }
 __device__ __forceinline__ float* smem_lo(float* s) { return s + 9 * PLANE1; }
 constexpr int LO_PLANE = (TILE / 2) * (TILE / 2);   // 256 low-res pixels per tile at level 1 (the largest staged level)
 // levels > 0: the low-resolution disp / flow / mask texels every halo pixel of the tile interpolates from, staged once
@@ -46,13 +48,16 @@ struct SsimOut {
 };
 
 // Stage B: thread = (column lane, 4-row run).  Returns the mixed reprojection loss
-// ssim_w*mean_c(SSIM) + l1_w*mean_c|y-x| (Trainer.py:413-423, tools.py:243-257) per frame.
+// ssim_w*mean_c(SSIM) + l1_w*mean_c|y-x| (Trainer.py:413-423, tools.py:243-257) per frame.  The statistics of the two
+// source frames are carried as packed pairs (frame 0, frame 1): sums, products and the SSIM rational run as
+// FADD2 / FMUL2 / FFMA2, i.e. one issue slot for both frames; target-only statistics stay scalar.
 template <int F>
-__device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const float* __restrict__ X0,
-                                            const float* __restrict__ X1, int lane, int row0, float ssim_w,
-                                            float l1_w, SsimOut& out) {
+__device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const float* __restrict__ XI, int lane, int row0,
+                                            float ssim_w, float l1_w, SsimOut& out) {
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
   const float inv9 = 1.f / 9.f, inv3 = 1.f / 3.f;   // window / channel means as multiplies (<= 1 ulp from the divisions)
+  const f32x2 inv9_2 = pack2(inv9, inv9), ninv9_2 = pack2(-inv9, -inv9);
+  const f32x2 C1_2 = pack2(C1, C1), C2_2 = pack2(C2, C2), two_2 = pack2(2.f, 2.f), one_2 = pack2(1.f, 1.f), half_2 = pack2(0.5f, 0.5f);
   float ssim_acc[2][4], l1_acc[2][4];
 #pragma unroll
   for (int f = 0; f < 2; ++f)
@@ -62,52 +67,52 @@ __device__ __forceinline__ void ssim_l1_run(const float* __restrict__ Y, const f
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     const float* Yc = Y + ch * PLANE1;
+    const float* Xc = XI + ch * PLANE1 * 2;
     float ay = 0.f, by = 0.f, ayy = 0.f, byy = 0.f;
-    float ax[2] = {0.f, 0.f}, bx[2] = {0.f, 0.f}, axx[2] = {0.f, 0.f}, bxx[2] = {0.f, 0.f}, axy[2] = {0.f, 0.f},
-          bxy[2] = {0.f, 0.f};
-    float yc_prev = 0.f, xc_prev[2] = {0.f, 0.f};
+    f32x2 ax = 0ull, bx = 0ull, axx = 0ull, bxx = 0ull, axy = 0ull, bxy = 0ull;
+    float yc_prev = 0.f;
+    f32x2 xc_prev = 0ull;
 #pragma unroll
     for (int rr = 0; rr < 6; ++rr) {
       const int o = (row0 + rr) * PITCH1 + lane;
       const float yl = Yc[o], yc = Yc[o + 1], yr = Yc[o + 2];
+      const f32x2 xl = *reinterpret_cast<const f32x2*>(Xc + 2 * o), xc = *reinterpret_cast<const f32x2*>(Xc + 2 * o + 2),
+                  xr = *reinterpret_cast<const f32x2*>(Xc + 2 * o + 4);
       const float hy = yl + yc + yr;
       const float hyy = yl * yl + yc * yc + yr * yr;
-      float hx[2], hxx[2], hxy[2], xcen[2];
-#pragma unroll
-      for (int f = 0; f < F; ++f) {
-        const float* Xc = (f == 0 ? X0 : X1) + ch * PLANE1;
-        const float xl = Xc[o], xc = Xc[o + 1], xr = Xc[o + 2];
-        hx[f] = xl + xc + xr;
-        hxx[f] = xl * xl + xc * xc + xr * xr;
-        hxy[f] = xl * yl + xc * yc + xr * yr;
-        xcen[f] = xc;
-      }
+      const f32x2 hx = add2(add2(xl, xc), xr);
+      const f32x2 hxx = fma2(xr, xr, fma2(xc, xc, mul2(xl, xl)));
+      const f32x2 hxy = fma2(xr, pack2(yr, yr), fma2(xc, pack2(yc, yc), mul2(xl, pack2(yl, yl))));
       if (rr >= 2) {
         const int k = rr - 2;   // output row row0+k, centre halo row row0+k+1 == previous iteration
         const float mu_y = (ay + hy) * inv9;
         const float e_yy = (ayy + hyy) * inv9;
         const float sig_y = e_yy - mu_y * mu_y;
-#pragma unroll
-        for (int f = 0; f < F; ++f) {
-          const float mu_x = (ax[f] + hx[f]) * inv9;
-          const float sig_x = (axx[f] + hxx[f]) * inv9 - mu_x * mu_x;
-          const float sig_xy = (axy[f] + hxy[f]) * inv9 - mu_x * mu_y;
-          const float n = (2.f * mu_x * mu_y + C1) * (2.f * sig_xy + C2);
-          const float dn = (mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2);
-          const float s = fminf(fmaxf((1.f - n * rcp_nr(dn)) * 0.5f, 0.f), 1.f);
-          ssim_acc[f][k] += s;
-          l1_acc[f][k] += fabsf(yc_prev - xc_prev[f]);
-        }
+        const f32x2 sx = add2(ax, hx);
+        const f32x2 mu_x = mul2(sx, inv9_2), nmu_x = mul2(sx, ninv9_2);
+        const f32x2 nsig_x = fma2(mu_x, mu_x, mul2(add2(axx, hxx), ninv9_2));          // -(E[xx] - mu_x^2)
+        const f32x2 sig_xy = fma2(nmu_x, pack2(mu_y, mu_y), mul2(add2(axy, hxy), inv9_2));
+        const f32x2 n = mul2(fma2(mu_x, pack2(2.f * mu_y, 2.f * mu_y), C1_2), fma2(sig_xy, two_2, C2_2));
+        const float dy1 = mu_y * mu_y + C1, ndy2 = -(sig_y + C2);
+        const f32x2 ndn = mul2(fma2(mu_x, mu_x, pack2(dy1, dy1)), add2(nsig_x, pack2(ndy2, ndy2)));   // -dn
+        float nd0, nd1;
+        unpack2(ndn, nd0, nd1);
+        const f32x2 nr = pack2(rcp_nr(nd0), rcp_nr(nd1));                                 // -1/dn
+        float s0, s1;
+        unpack2(mul2(fma2(n, nr, one_2), half_2), s0, s1);                                // (1 - n/dn)/2
+        ssim_acc[0][k] += __saturatef(s0);
+        ssim_acc[1][k] += __saturatef(s1);
+        float d0, d1;
+        unpack2(add2(xc_prev, pack2(-yc_prev, -yc_prev)), d0, d1);
+        l1_acc[0][k] += fabsf(d0);
+        l1_acc[1][k] += fabsf(d1);
       }
       ay = by + hy, by = hy, ayy = byy + hyy, byy = hyy;
       yc_prev = yc;
-#pragma unroll
-      for (int f = 0; f < F; ++f) {
-        ax[f] = bx[f] + hx[f], bx[f] = hx[f];
-        axx[f] = bxx[f] + hxx[f], bxx[f] = hxx[f];
-        axy[f] = bxy[f] + hxy[f], bxy[f] = hxy[f];
-        xc_prev[f] = xcen[f];
-      }
+      ax = add2(bx, hx), bx = hx;
+      axx = add2(bxx, hxx), bxx = hxx;
+      axy = add2(bxy, hxy), bxy = hxy;
+      xc_prev = xc;
     }
   }
 #pragma unroll
@@ -147,9 +152,9 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         const float* src = d.source[f] + (size_t)b * 3 * P;
-        float* X = smem_X(smem, f);
+        float* X = smem_XI(smem) + f;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) X[ch * PLANE1 + hr * PITCH1 + hc] = __ldg(src + ch * P + o);
+        for (int ch = 0; ch < 3; ++ch) X[(ch * PLANE1 + hr * PITCH1 + hc) * 2] = __ldg(src + ch * P + o);
       }
     }
   }
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
   const float l1_w = 1.f - d.ssim_weight;
   SsimOut ident;
   if (automask) {   // identity reprojection losses (Trainer.py:327-333), level independent
-    ssim_l1_run<F>(Y, smem_X(smem, 0), smem_X(smem, 1), lane, warp * 4, d.ssim_weight, l1_w, ident);
+    ssim_l1_run<F>(Y, smem_XI(smem), lane, warp * 4, d.ssim_weight, l1_w, ident);
     __syncthreads();
   }
 
@@ -247,12 +252,12 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
         frame_geometry<MODE>(g, pg, &cam, f, cf, m, H, W, interior);
         const Foot ft = footprint(unnormalise(g.gx, W), unnormalise(g.gy, H), H, W);
         const float* src = d.source[f] + (size_t)b * 3 * P;
-        float* X = smem_X(smem, f);
+        float* X = smem_XI(smem) + f;
         float col[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           col[ch] = sample_plane(src + ch * P, W, ft);                  // Trainer.py:281
-          X[ch * PLANE1 + hr * PITCH1 + hc] = col[ch];
+          X[(ch * PLANE1 + hr * PITCH1 + hc) * 2] = col[ch];
         }
         if (interior) {
           if (MODE >= 1) {
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
     float s_photo = 0.f, s_ident = 0.f;
     {
       SsimOut wl;
-      ssim_l1_run<F>(Y, smem_X(smem, 0), smem_X(smem, 1), lane, warp * 4, d.ssim_weight, l1_w, wl);
+      ssim_l1_run<F>(Y, smem_XI(smem), lane, warp * 4, d.ssim_weight, l1_w, wl);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int r = r0 + warp * 4 + k, c = c0 + lane;

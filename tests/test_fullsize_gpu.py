@@ -84,38 +84,60 @@ def loss_from_sums(case, cfg, sums, B):
     return loss, terms
 
 
+def _oracle(case, cfg, dtype):
+    o_in, o_out, o_leaves, o_noise = case.tensors("cpu")
+    if dtype == torch.float64:
+        o_in = {k: (v.double() if v.is_floating_point() else v) for k, v in o_in.items()}
+        o_leaves = {k: v.detach().double().requires_grad_(True) for k, v in o_leaves.items()}
+        o_out = {}
+        for k, t in o_leaves.items():
+            if k[0] == "motion_prob":
+                for f in FRAMES:
+                    o_out[("motion_prob", f, k[1])] = t
+                    o_out[("motion_mask", f, k[1])] = torch.sigmoid(t)
+            else:
+                o_out[k] = t
+        o_noise = None if o_noise is None else {s: n.double() for s, n in o_noise.items()}
+    vs.generate_images_pred(cfg, o_in, o_out)
+    losses = vs.compute_losses(cfg, o_in, o_out, case.step, case.steps_per_epoch, noise=o_noise)
+    losses["loss"].backward()
+    return losses, {k: v.grad for k, v in o_leaves.items() if v.grad is not None}
+
+
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_full_resolution_loss_and_grads_vs_oracle(name):
+    """Loss terms: 1e-4 relative against the fp32 oracle (north_star).  Gradients: the per-pixel argmin / floor decisions
+    make them sensitive to last-ulp differences at this image size (the oracle evaluated in fp32 and in fp64 differs by
+    up to ~0.5 % in the pose gradient of the automask configuration), so the bar is "as close to the fp64 oracle as the
+    reference's own fp32 arithmetic is": error vs fp64 <= 2x the fp32 oracle's error vs fp64 (floors from oracle/compare.py)."""
+    from oracle.compare import robust_report
+
     case = SynthCase(name, batch=2)
     cfg = vs.LossConfig(case.H, case.W, case.scales, phase=case.phase, **PHOTO_ONLY)
-    # oracle, CPU fp32
-    o_in, o_out, o_leaves, o_noise = case.tensors("cpu")
-    vs.generate_images_pred(cfg, o_in, o_out)
-    o_losses = vs.compute_losses(cfg, o_in, o_out, case.step, case.steps_per_epoch, noise=o_noise)
-    o_losses["loss"].backward()
+    o_losses, g32 = _oracle(case, cfg, torch.float32)
+    _, g64 = _oracle(case, cfg, torch.float64)
     # CUDA path through the C ABI
     g_in, g_out, g_leaves, g_noise = case.tensors("cuda")
     sums = kernel_sums(case, cfg, g_in, g_out, g_noise)
     loss, terms = loss_from_sums(case, cfg, sums, case.B)
     loss.backward()
     torch.cuda.synchronize()
-    assert float(loss) == pytest.approx(float(o_losses["loss"]), rel=1e-4)
-    assert float(terms["p_photo"]) == pytest.approx(float(o_losses["loss_term/p_photo"]), rel=1e-4)
+    assert float(loss.detach()) == pytest.approx(float(o_losses["loss"].detach()), rel=1e-4)
+    assert float(terms["p_photo"].detach()) == pytest.approx(float(o_losses["loss_term/p_photo"].detach()), rel=1e-4)
     if cfg.bool_MotMask:
-        assert float(terms["c_consistency"]) == pytest.approx(float(o_losses["loss_term/c_consistency"]), rel=1e-4)
-    for k, ref in o_leaves.items():
-        if ref.grad is None:
-            continue
+        assert float(terms["c_consistency"].detach()) == pytest.approx(float(o_losses["loss_term/c_consistency"].detach()), rel=1e-4)
+    for k, ref in g64.items():
         got = g_leaves[k].grad
         assert got is not None, k
-        if k[0] == "cam_T_cam":
-            assert_close_robust(got.cpu(), ref.grad, rtol=2e-3, max_outlier_frac=0.0, max_rel_l2=2e-3, what=k)
-        else:
-            # floor()/argmin flips (oracle/compare.py) happen per FULL-resolution pixel, and each one perturbs ~3x3 full-
-            # resolution gradients = up to ~16 samples of a coarse map, so the share of perturbed samples of a level-s
-            # map grows like 4^s at a fixed image size; the integrated error (rel_l2) stays bounded as everywhere else
-            s_lvl = k[-1] if isinstance(k[-1], int) and k[0] != "cam_T_cam" else 0
-            assert_close_robust(got.cpu(), ref.grad, rtol=2e-4, max_outlier_frac=min(2e-3 * 4**s_lvl, 3e-2), what=k)
+        pose = k[0] == "cam_T_cam"
+        rtol = 2e-3 if pose else 2e-4
+        ours, base = robust_report(got.cpu(), ref, rtol), robust_report(g32[k], ref, rtol)
+        s_lvl = 0 if pose else k[-1]
+        # floors: integrated error as in the golden tests; the share of perturbed samples of a level-s map grows like 4^s
+        # at a fixed image size (one flipped full-resolution pixel touches ~16 samples of a coarse map)
+        assert ours["rel_l2"] <= max(2 * base["rel_l2"], 2e-3 if pose else 2e-2), (k, ours, base)
+        if not pose:
+            assert ours["outlier_frac"] <= max(2 * base["outlier_frac"], min(2e-3 * 4**s_lvl, 3e-2)), (k, ours, base)
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
