@@ -306,6 +306,115 @@ __global__ void __launch_bounds__(CONV_THREADS, 4) conv_core_kernel(const __grid
   }
 }
 
+// ---- 3x3 layers with few output channels (disparity heads, full-resolution motion level, their data gradients) ----
+// The 8x16-pixel x 8-channel-group mapping of conv_core_kernel leaves most lanes idle when Cout <= 16, and these layers
+// are bound by the input stream, not by FMAs.  Here every thread owns 4 consecutive pixels x ALL output channels
+// (CO = 2/4/12/16, FFMA2 on channel pairs), reads its 3x6 input window straight from global memory (neighbouring
+// threads share the lines through L1) and takes the weights of a 16-channel chunk from shared memory.
+// CTA = 256 threads = 16 rows x 64 columns of the output.  Inputs without up-sampling only (x0 and x1 share the grid).
+constexpr int SM_TH = 16, SM_TW = 64, SM_THREADS = 256, SM_CI = 16;
+
+template <int CO>
+__global__ void __launch_bounds__(SM_THREADS, 2) conv_small_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int CP = CO / 2;
+  __shared__ __align__(16) float w_s[SM_CI * 9 * CO];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = (tid & 15) * 4;
+  const int tile = blockIdx.x;
+  const int y = (tile / a.tiles_x) * SM_TH + ty, x0p = (tile % a.tiles_x) * SM_TW + tx;
+  const int b = blockIdx.z;
+  const int Hin = a.vin.Hin, Win = a.vin.Win, C0 = a.vin.C0, Cin = a.Cin;
+  const size_t plane = (size_t)Hin * Win;
+  const bool reflect = a.vin.pad_mode == DD_PAD_REFLECT;
+
+  // source offsets of the 3 rows / 6 columns this thread reads (channel independent); -1 = zero (padding / overhang)
+  int ro[3], co[6];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    int yy = y + dy - 1 + a.oy;
+    if (reflect && yy >= -1 && yy <= Hin) yy = reflect1(yy, Hin);
+    ro[dy] = (yy >= 0 && yy < Hin) ? yy * Win : -1;
+  }
+#pragma unroll
+  for (int dx = 0; dx < 6; ++dx) {
+    int xx = x0p + dx - 1 + a.ox;
+    if (reflect && xx >= -1 && xx <= Win) xx = reflect1(xx, Win);
+    co[dx] = (xx >= 0 && xx < Win) ? xx : -1;
+  }
+
+  f32x2 acc[CP][4];
+#pragma unroll
+  for (int c = 0; c < CP; ++c)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[c][p] = 0ull;
+
+  const float* src0 = a.vin.x0 + (size_t)b * C0 * plane;
+  const float* src1 = a.vin.x1 ? a.vin.x1 + ((ptrdiff_t)b * a.vin.C1 - C0) * (ptrdiff_t)plane : a.vin.x0;
+  for (int ci0 = 0; ci0 < Cin; ci0 += SM_CI) {
+    __syncthreads();   // previous chunk's weights no longer read
+    const int chunk_floats = min(SM_CI, Cin - ci0) * 9 * CO;   // weights of channels >= Cin are never read below
+    for (int i = tid; i < SM_CI * 9 * CO / 4; i += SM_THREADS) {
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i * 4 < chunk_floats) w4 = __ldg(reinterpret_cast<const float4*>(a.wt + (size_t)ci0 * 9 * CO) + i);
+      reinterpret_cast<float4*>(w_s)[i] = w4;
+    }
+    __syncthreads();
+    const int nci = min(SM_CI, Cin - ci0);
+    for (int ci = 0; ci < nci; ++ci) {
+      const int c = ci0 + ci;
+      const float* pl = (c < C0 ? src0 : src1) + (size_t)c * plane;
+      const float* wc = w_s + ci * 9 * CO;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        float v[6];
+#pragma unroll
+        for (int dx = 0; dx < 6; ++dx) v[dx] = (ro[dy] >= 0 && co[dx] >= 0) ? __ldg(pl + ro[dy] + co[dx]) : 0.f;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          f32x2 w2[CP];
+#pragma unroll
+          for (int q = 0; q < CP; ++q) w2[q] = *reinterpret_cast<const f32x2*>(wc + (dy * 3 + dx) * CO + 2 * q);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const f32x2 vv = pack2(v[p + dx], v[p + dx]);
+#pragma unroll
+            for (int q = 0; q < CP; ++q) acc[q][p] = fma2(w2[q], vv, acc[q][p]);
+          }
+        }
+      }
+    }
+  }
+
+  if (y >= a.Ho || x0p >= a.Wo) return;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    if (c >= a.Cout) continue;
+    const float bv = a.bias ? __ldg(a.bias + c) : 0.f;
+    float* outp = a.out;
+    size_t o = (((size_t)b * a.Cout + c) * a.Ho + y) * a.Wo + x0p;
+    if (a.split > 0) {   // two destination tensors with split / Cout-split channels
+      if (c < a.split) o = (((size_t)b * a.split + c) * a.Ho + y) * a.Wo + x0p;
+      else outp = a.out1, o = (((size_t)b * (a.Cout - a.split) + (c - a.split)) * a.Ho + y) * a.Wo + x0p;
+      if (outp == nullptr) continue;
+    }
+    float r[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float lo, hi;
+      unpack2(acc[c >> 1][p], lo, hi);
+      r[p] = apply_act(((c & 1) ? hi : lo) + bv, a.act);
+      if (a.residual && x0p + p < a.Wo) r[p] += __ldg(a.residual + o + p);
+    }
+    if (x0p + 3 < a.Wo && (a.Wo & 3) == 0) {
+      *reinterpret_cast<float4*>(outp + o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (x0p + p < a.Wo) outp[o + p] = r[p];
+    }
+  }
+}
+
 // wt[ci][tap][co] (zero padded to cout_pad) from OIHW weights; `transpose` builds the data-gradient
 // operator: wt[co_f][8-tap][ci_f] (flipped taps, swapped channel roles).
 __global__ void conv_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int KK,
@@ -1022,6 +1131,25 @@ static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, 
     return DD_OK;
   }
   const int KK = ks * ks;
+  static const bool no_small = getenv("DD_NO_SMALL_CONV") != nullptr;
+  if (!no_small && ks == 3 && args.Cout <= 16 && args.vin.up0 == DD_UP_NONE) {
+    const int co_t = args.Cout <= 2 ? 2 : (args.Cout <= 4 ? 4 : (args.Cout <= 12 ? 12 : 16));
+    args.cout_pad = co_t;
+    const size_t wn = (size_t)args.Cin * KK * co_t;
+    conv_prep_weights_kernel<<<(int)((wn + 255) / 256 < 592 ? (wn + 255) / 256 : 592), 256, 0, st>>>(
+        w_oihw, wt_buf, Cout_f, Cin_f, KK, co_t, transpose ? 1 : 0); dd::count_launches(1);
+    args.wt = wt_buf;
+    args.tiles_x = (args.Wo + SM_TW - 1) / SM_TW;
+    const int tiles_y = (args.Ho + SM_TH - 1) / SM_TH;
+    dim3 grid(args.tiles_x * tiles_y, 1, args.B);
+    if (co_t == 2) conv_small_kernel<2><<<grid, SM_THREADS, 0, st>>>(args);
+    else if (co_t == 4) conv_small_kernel<4><<<grid, SM_THREADS, 0, st>>>(args);
+    else if (co_t == 12) conv_small_kernel<12><<<grid, SM_THREADS, 0, st>>>(args);
+    else conv_small_kernel<16><<<grid, SM_THREADS, 0, st>>>(args);
+    dd::count_launches(1);
+    DD_CHECK_CUDA(cudaGetLastError());
+    return DD_OK;
+  }
   const int cpt = cpt_for(args.Cout);
   args.cout_pad = round_up(args.Cout, 8 * cpt);
   const size_t wn = (size_t)args.Cin * KK * args.cout_pad;

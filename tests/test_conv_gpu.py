@@ -40,6 +40,9 @@ CASES = [
     (2, 70, 0, 48, 6, 20, 1, "zero", "relu", "none", False),
     (2, 40, 0, 40, 6, 20, 3, "zero", "relu", "none", False),
     (1, 128, 64, 112, 24, 80, 3, "reflect", "elu", "bilinear", False),
+    (2, 3, 9, 9, 10, 18, 3, "zero", "none", "none", False),       # few output channels, width not a multiple of 4
+    (1, 5, 0, 12, 7, 9, 3, "reflect", "elu", "none", False),      # odd sizes, reflection inside a partial tile
+    (2, 20, 0, 3, 34, 70, 3, "zero", "none", "none", True),       # several tiles, residual, 3 outputs
 ]
 
 
