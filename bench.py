@@ -190,8 +190,13 @@ def run_ours(args):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         last = None
+        staged = tr.prefetch(dict(batches[0])) if e2e else None
         for i in range(steps):
-            outputs, losses = tr.train_step(dict(batches[i % len(batches)]))
+            if e2e:   # this step's batch was staged by the copy stream; the next one is issued before the step runs
+                cur_batch, staged = staged, (tr.prefetch(dict(batches[(i + 1) % len(batches)])) if i + 1 < steps else None)
+            else:
+                cur_batch = dict(batches[i % len(batches)])
+            outputs, losses = tr.train_step(cur_batch)
             if e2e:
                 last = float(losses["loss"].detach().cpu())      # device -> host read of the step's result
             del outputs

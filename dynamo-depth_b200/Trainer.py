@@ -334,9 +334,36 @@ class Trainer:
         return depth_to_disp(gd, self.opt.min_depth, self.opt.max_depth), gd
 
     # ------------------------------------------------------------------ inputs / checkpoints / misc
+    def prefetch(self, inputs):
+        """Start the host -> device copies of a (pinned) batch on a dedicated copy stream so that they overlap the
+        training step in flight; returns the device-side dict to hand to train_step / process_batch, which waits for
+        the copies (an event, no host synchronisation) before touching the tensors."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        dev, moved = {}, {}
+        with torch.cuda.stream(self._copy_stream):
+            for key, inp in inputs.items():
+                if torch.is_tensor(inp) and inp.device != self.device:
+                    if id(inp) not in moved:
+                        moved[id(inp)] = inp.to(self.device, non_blocking=True)
+                    dev[key] = moved[id(inp)]
+                else:
+                    dev[key] = inp
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        dev["__ready__"] = (ready, list(moved.values()))
+        return dev
+
     def process_inputs(self, inputs):
         """host -> device first (non-blocking from pinned memory), then the colour pyramid on the GPU; the
         reference resizes on the CPU before the copy (Trainer.py:722-727), which sits on the critical path."""
+        pending = inputs.pop("__ready__", None)
+        if pending is not None:      # batch staged by prefetch(): order the compute stream after the copies
+            ready, tensors = pending
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ready)
+            for t in tensors:
+                t.record_stream(cur)
         moved = {}
         for key, inp in inputs.items():
             if torch.is_tensor(inp) and inp.device != self.device:

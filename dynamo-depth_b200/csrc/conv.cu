@@ -2,10 +2,13 @@
 //
 //   out = act( conv_k( pad( concat( up(x0), x1 ) ) ) + bias ) [+ residual]
 //
-// The "virtual input" (up-sampling, skip concatenation, reflection / zero padding) is never
+// The "virtual input" (nearest up-sampling, skip concatenation, reflection / zero padding) is never
 // materialised: the tile loader evaluates it while staging shared memory (layers.py:85-121,
-// depth_decoder.py:46-53,103-113, motion_decoder.py:34-62).  One CTA = 128 threads computes an
-// 8x16 pixel tile for 8*CPT output channels; every thread owns CPT channels x 8 consecutive pixels.
+// depth_decoder.py:46-53,103-113, motion_decoder.py:34-62); only bilinear x2 up-sampling is written once
+// to the workspace (materialise_up).  3x3 layers with more than 16 output channels run the Winograd
+// F(2x2,3x3) kernel, 3x3 layers with at most 16 the small-Cout kernel, everything else the direct core:
+// one CTA = 128 threads computes an 8x16 pixel tile for 8*CPT output channels, every thread owns CPT
+// channels x 8 consecutive pixels.
 // The data gradient reuses the same core on the (zero-extended) output gradient with flipped,
 // transposed weights, producing the gradient on the padded grid; a light routing kernel then folds
 // the reflection border back and transposes the up-sampling / concatenation.
@@ -30,27 +33,10 @@ struct VirtIn {
   int pad_mode;
 };
 
-__device__ __forceinline__ float virt_load(const VirtIn& v, int b, int ci, int y, int x) {
-  if (y < -1 || y > v.Hin || x < -1 || x > v.Win) return 0.f;   // outside even the padded grid (tile overhang)
-  if (v.pad_mode == DD_PAD_REFLECT) {
-    y = reflect1(y, v.Hin);
-    x = reflect1(x, v.Win);
-  } else if (y < 0 || y >= v.Hin || x < 0 || x >= v.Win) {
-    return 0.f;
-  }
-  if (ci < v.C0) {
-    const float* p = v.x0 + ((size_t)b * v.C0 + ci) * v.H0 * v.W0;
-    if (v.up0 == DD_UP_NONE) return __ldg(p + y * v.W0 + x);
-    if (v.up0 == DD_UP_NEAREST2) return __ldg(p + (y >> 1) * v.W0 + (x >> 1));   // F.interpolate nearest (layers.py:121)
-    const Taps ty = up_taps(y, 1, v.H0), tx = up_taps(x, 1, v.W0);               // bilinear x2 (depth_decoder.py:104)
-    return bilerp(p, v.W0, ty, tx);
-  }
-  return __ldg(v.x1 + (((size_t)b * v.C1 + (ci - v.C0)) * v.Hin + y) * v.Win + x);
-}
-
-// Per-CTA source map of one input tile: where every tile position reads from, independent of the channel.
-// Built once per CTA so the per-k-step staging is a table look-up + load instead of re-deriving padding,
-// reflection and up-sampling taps for every element of every channel.
+// Source of one position of an input tile, independent of the channel: derived once per thread (registers) so that
+// the per-K-step staging is an address add + load instead of re-deriving padding, reflection and up-sampling taps for
+// every element of every channel.  (Bilinear x2 up-sampling is materialised by the host wrapper before the conv
+// kernels run, so only o00 is live there; the four-tap form remains for completeness of the virtual-input model.)
 struct TapEntry {
   int o00, o01, o10, o11;   // offsets inside one x0 channel plane (o00 < 0: zero padding / outside)
   float ly, lx;             // bilinear weights (DD_UP_BILINEAR2 only)
@@ -78,21 +64,6 @@ __device__ __forceinline__ void build_tile_map(const VirtIn& v, int y, int x, Ta
     e0.o10 = ty.i1 * v.W0 + tx.i0, e0.o11 = ty.i1 * v.W0 + tx.i1;
     e0.ly = ty.l, e0.lx = tx.l;
   }
-}
-
-__device__ __forceinline__ float map_load(const VirtIn& v, int b, int cg, const TapEntry* __restrict__ tab0,
-                                          const int* __restrict__ tab1, int pos) {
-  if (cg < v.C0) {
-    const TapEntry e = tab0[pos];
-    if (e.o00 < 0) return 0.f;
-    const float* p = v.x0 + ((size_t)b * v.C0 + cg) * v.H0 * v.W0;
-    if (v.up0 != DD_UP_BILINEAR2) return __ldg(p + e.o00);
-    const float v00 = __ldg(p + e.o00), v01 = __ldg(p + e.o01), v10 = __ldg(p + e.o10), v11 = __ldg(p + e.o11);
-    return (1.f - e.ly) * ((1.f - e.lx) * v00 + e.lx * v01) + e.ly * ((1.f - e.lx) * v10 + e.lx * v11);
-  }
-  const int o = tab1[pos];
-  if (o < 0) return 0.f;
-  return __ldg(v.x1 + ((size_t)b * v.C1 + (cg - v.C0)) * v.Hin * v.Win + o);
 }
 
 struct ConvArgs {

@@ -66,3 +66,27 @@ def test_trainer_pyramid_uses_kernel_and_matches_host_chain():
     assert L.load().dd_launch_count() - n0 == len([s for s in opt.scales if s != 0])
     for s in opt.scales:
         assert (dev[("color", 0, s)].cpu() - host[("color", 0, s)]).abs().max().item() <= 2e-6
+
+
+def test_prefetched_batch_equals_direct_batch():
+    """Trainer.prefetch (copy stream + event) must hand process_batch the same tensors as the in-line copy."""
+    import options
+    from Trainer import Trainer
+    from dd_b200 import synthetic
+
+    opt = options.DynamoOptions().parse(args=["-d", "waymo", "--depth_model", "litemono", "--weights_init", "scratch", "--height", "64",
+                                              "--width", "96", "-b", "2"])
+    opt.cuda_ids, opt.local_rank, opt.ddp = [0], 0, False
+    tr = Trainer(opt)
+    batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in synthetic.make_batch(opt, 9).items()}
+    direct = dict(batch)
+    tr.process_inputs(direct)
+    staged = tr.prefetch(dict(batch))
+    assert "__ready__" in staged
+    tr.process_inputs(staged)
+    assert "__ready__" not in staged
+    torch.cuda.synchronize()
+    assert set(staged) == set(direct)
+    for k, v in direct.items():
+        if torch.is_tensor(v):
+            assert staged[k].device == v.device and torch.equal(staged[k], v), k
