@@ -83,3 +83,37 @@ def test_ground_score_kernel_matches_torch():
         x, y, z = flat[k % B]
         ref[k] = int(((x * w[k, 0] + z * w[k, 1] + w[k, 2] - y).abs() < tol).sum())
     assert (got.cpu() - ref).abs().max().item() <= 1   # a threshold comparison may flip in the last ulp
+
+
+@pytest.mark.parametrize("phase", ["disp_init", "fine_tune"])
+def test_ragged_last_batch(phase):
+    """A last batch smaller than opt.batch_size must work (the reference slices its per-batch buffers with [:B],
+    tools.py:191-197) and give, per image, what the full batch gives: losses are means, so the loss of the first
+    image alone must equal the single-image evaluation, and the step on a 1-image batch must run end to end."""
+    import options
+    from Trainer import Trainer
+    from dd_b200 import synthetic
+
+    opt = options.DynamoOptions().parse(args=["-d", "waymo", "--depth_model", "litemono", "--weights_init", "scratch", "--height", "64",
+                                              "--width", "96", "-b", "3", "--g_d_ground", "0.0"])
+    opt.cuda_ids, opt.local_rank, opt.ddp = [0], 0, False
+    torch.manual_seed(3)
+    tr = Trainer(opt)
+    tr.setup_phase(phase)
+    tr.bool_automask = False          # no device-side tie-break noise: deterministic comparison
+    tr.step, tr.num_steps_per_epoch = 100, 100
+    tr.set_eval()                      # BatchNorm running statistics, no DropPath: per-image results independent of the batch
+    full = {k: v.cuda() for k, v in synthetic.make_batch(opt, 4).items()}
+    one = {k: v[:1].contiguous() for k, v in full.items()}
+    with torch.no_grad():
+        _, l_full = tr.process_batch(dict(full))
+        _, l_one = tr.process_batch(dict(one))
+        per_image = []
+        for i in range(3):
+            _, li = tr.process_batch({k: v[i:i + 1].contiguous() for k, v in full.items()})
+            per_image.append(float(li["loss_term/p_photo"]))
+    assert float(l_one["loss_term/p_photo"]) == pytest.approx(per_image[0], rel=1e-6)
+    assert float(l_full["loss_term/p_photo"]) == pytest.approx(sum(per_image) / 3, rel=2e-5)
+    tr.set_train()
+    outputs, losses = tr.train_step(dict(one))     # backward + optimiser on the ragged batch
+    assert torch.isfinite(losses["loss"]).item()
