@@ -984,6 +984,228 @@ __global__ void __launch_bounds__(CONV_THREADS) conv_wgrad_kernel(const __grid_c
   }
 }
 
+// ---- weight gradient in the Winograd domain (3x3 layers with > 16 output and >= 8 input channels) ----------------
+// dW = G^T [ sum over tiles (A dY A^T) (.) (B^T d B) ] G: the same F(2x2,3x3) transforms as the forward kernel, 2.25x
+// fewer multiplies than the direct weight gradient.  CTA = 256 threads owns 32 output x 32 input channels and walks a
+// contiguous range of K-steps; one K-step = 8 Winograd tiles (a 4x8 block of output pixels of one image).  Per step and
+// frequency the product [32 co x 8 tiles] x [8 tiles x 32 ci] accumulates into thread = (frequency, 8 co, 8 ci) with
+// FFMA2 on input-channel pairs — the GEMM of conv_wino_kernel with the transformed output gradient in the role of the
+// weights.  Same one-barrier software pipeline: step k+2 is gathered into registers, step k+1 transformed, step k
+// multiplied; half of the warps run transform and GEMM in the opposite order.
+constexpr int WW_CH = 32;                      // channels per CTA on either side
+constexpr int WW_KT = 8;                       // tiles per K-step: 2 tile rows x 4 tile columns
+constexpr int WW_IN_R = 6, WW_IN_C = 10;       // input patch of a step (4x8 outputs + halo)
+constexpr int WW_IN_PITCH = 12;
+constexpr int WW_IN_PLANE = WW_IN_R * WW_IN_PITCH + 4;   // 76
+constexpr int WW_G_PLANE = 36;                 // 4x8 gradient block (+4)
+constexpr int WW_TP = 36;                      // pitch over channels of the transformed operands
+constexpr int WW_SMEM_LOOP = 2 * WW_CH * WW_IN_PLANE + 2 * WW_CH * WW_G_PLANE + 2 * 2 * 16 * WW_KT * WW_TP;
+constexpr int WW_SMEM_EPI = 16 * WW_CH * 33;
+constexpr int WW_SMEM_FLOATS = WW_SMEM_LOOP > WW_SMEM_EPI ? WW_SMEM_LOOP : WW_SMEM_EPI;
+
+struct WinoWgradArgs {
+  VirtIn vin;
+  const float* g;
+  int B, H, W, Cin, Cout;
+  int nbr, nbc;          // 4x8 pixel blocks per image (rows, columns)
+  int steps_per_split;
+  float* gw;
+};
+
+__global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __grid_constant__ WinoWgradArgs a) {
+  extern __shared__ __align__(16) float wsm[];
+  float* in_s = wsm;                                   // [2][32 ci][WW_IN_PLANE]
+  float* g_s = in_s + 2 * WW_CH * WW_IN_PLANE;         // [2][32 co][WW_G_PLANE]
+  float* V_s = g_s + 2 * WW_CH * WW_G_PLANE;           // [2][16][8 tiles][WW_TP]  transformed input (ci inner)
+  float* D_s = V_s + 2 * 16 * WW_KT * WW_TP;           // [2][16][8 tiles][WW_TP]  transformed output gradient (co inner)
+  float* M_s = wsm;                                    // epilogue: [16][32 co][33]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int co0 = blockIdx.x * WW_CH, ci0 = blockIdx.y * WW_CH;
+  const int per_img = a.nbr * a.nbc;
+  const int n_total = a.B * per_img;
+  const int s0 = blockIdx.z * a.steps_per_split;
+  const int nk = min(a.steps_per_split, n_total - s0);
+  if (nk <= 0) return;
+  // GEMM role: frequency p, 8 output channels (cg), 8 input channels (tg)
+  const int p = 2 * warp + (lane >> 4), cg = (lane >> 2) & 3, tg = lane & 3;
+  // transform role: channel tc (input channel and output channel alike), tile tt of the step
+  const int tc = tid >> 3, tt = tid & 7, ttr = tt >> 2, ttc = tt & 3;
+  // loader roles: input patch position ipos (60 valid) x 8 channels (quarter iq); gradient pixel gpx x 4 channels (gq)
+  const int ipos = tid & 63, iq = tid >> 6;
+  const int ir = ipos / WW_IN_C, ic = ipos - ir * WW_IN_C;
+  const bool ipos_ok = ipos < WW_IN_R * WW_IN_C;
+  const int gpx = tid & 31, gq = tid >> 5;
+  const int gr = gpx >> 3, gc = gpx & 7;
+  const int C0 = a.vin.C0;
+  const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win, gplane = (size_t)a.H * a.W;
+
+  f32x2 acc2[8][4];   // [output channel][input-channel pair]
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc2[c][t] = 0ull;
+
+  auto gather = [&](int s, float (&pin)[8], float (&pg)[4]) {
+    const int b = s / per_img, rem = s - b * per_img;
+    const int br = rem / a.nbc, bc = rem - br * a.nbc;
+    TapEntry te;
+    int o1;
+    build_tile_map(a.vin, 4 * br + ir - 1, 8 * bc + ic - 1, te, o1);
+    const bool ok0 = ipos_ok && te.o00 >= 0, ok1 = ipos_ok && o1 >= 0 && a.vin.x1 != nullptr;
+    const int cb = ci0 + iq * 8;
+    const float* q0 = a.vin.x0 + ((size_t)b * C0 + cb) * plane0 + (ok0 ? te.o00 : 0);
+    const float* q1 = ok1 ? a.vin.x1 + ((ptrdiff_t)b * a.vin.C1 + (cb - C0)) * (ptrdiff_t)plane1 + o1 : a.vin.x0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb + j;
+      const bool in0 = c < C0;
+      const bool ok = in0 ? ok0 : (ok1 && c < a.Cin);
+      float v = 0.f;
+      if (ok) v = __ldg(in0 ? q0 : q1);
+      pin[j] = v;
+      q0 += plane0, q1 += plane1;
+    }
+    const int y = 4 * br + gr, x = 8 * bc + gc;
+    const bool gok = y < a.H && x < a.W;
+    const float* gp = a.g + ((size_t)b * a.Cout + co0 + gq * 4) * gplane + (gok ? (size_t)y * a.W + x : 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pg[j] = (gok && co0 + gq * 4 + j < a.Cout) ? __ldg(gp) : 0.f;
+      gp += gplane;
+    }
+  };
+  auto scatter = [&](int buf, const float (&pin)[8], const float (&pg)[4]) {
+    if (ipos_ok) {
+      float* dst = in_s + buf * WW_CH * WW_IN_PLANE + (iq * 8) * WW_IN_PLANE + ir * WW_IN_PITCH + ic;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j * WW_IN_PLANE] = pin[j];
+    }
+    float* gd = g_s + buf * WW_CH * WW_G_PLANE + (gq * 4) * WW_G_PLANE + gr * 8 + gc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gd[j * WW_G_PLANE] = pg[j];
+  };
+  // V = B^T d B of (input channel tc, tile tt) and dM = A dY A^T of (output channel tc, tile tt): buffers sb -> tb
+  auto transform = [&](int sb, int tb) {
+    {
+      const float* dp = in_s + sb * WW_CH * WW_IN_PLANE + tc * WW_IN_PLANE + (2 * ttr) * WW_IN_PITCH + 2 * ttc;
+      float d[4][4], t[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 lo = *reinterpret_cast<const float2*>(dp + i * WW_IN_PITCH);
+        const float2 hi = *reinterpret_cast<const float2*>(dp + i * WW_IN_PITCH + 2);
+        d[i][0] = lo.x, d[i][1] = lo.y, d[i][2] = hi.x, d[i][3] = hi.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[0][j] = d[0][j] - d[2][j];
+        t[1][j] = d[1][j] + d[2][j];
+        t[2][j] = d[2][j] - d[1][j];
+        t[3][j] = d[1][j] - d[3][j];
+      }
+      float* vp = V_s + tb * 16 * WW_KT * WW_TP + tt * WW_TP + tc;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        vp[(i * 4 + 0) * WW_KT * WW_TP] = t[i][0] - t[i][2];
+        vp[(i * 4 + 1) * WW_KT * WW_TP] = t[i][1] + t[i][2];
+        vp[(i * 4 + 2) * WW_KT * WW_TP] = t[i][2] - t[i][1];
+        vp[(i * 4 + 3) * WW_KT * WW_TP] = t[i][1] - t[i][3];
+      }
+    }
+    {
+      const float* gp = g_s + sb * WW_CH * WW_G_PLANE + tc * WW_G_PLANE + (2 * ttr) * 8 + 2 * ttc;
+      const float2 y0 = *reinterpret_cast<const float2*>(gp), y1 = *reinterpret_cast<const float2*>(gp + 8);
+      const float r[4][2] = {{y0.x, y0.y}, {y0.x + y1.x, y0.y + y1.y}, {y0.x - y1.x, y0.y - y1.y}, {-y1.x, -y1.y}};
+      float* dp = D_s + tb * 16 * WW_KT * WW_TP + tt * WW_TP + tc;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        dp[(i * 4 + 0) * WW_KT * WW_TP] = r[i][0];
+        dp[(i * 4 + 1) * WW_KT * WW_TP] = r[i][0] + r[i][1];
+        dp[(i * 4 + 2) * WW_KT * WW_TP] = r[i][0] - r[i][1];
+        dp[(i * 4 + 3) * WW_KT * WW_TP] = -r[i][1];
+      }
+    }
+  };
+  auto gemm = [&](int buf) {
+    const float* up = D_s + buf * 16 * WW_KT * WW_TP + p * WW_KT * WW_TP + cg * 8;
+    const float* vp = V_s + buf * 16 * WW_KT * WW_TP + p * WW_KT * WW_TP + tg * 8;
+#pragma unroll 2
+    for (int k = 0; k < WW_KT; ++k) {
+      const float4 u0 = *reinterpret_cast<const float4*>(up + k * WW_TP), u1 = *reinterpret_cast<const float4*>(up + k * WW_TP + 4);
+      const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(vp + k * WW_TP), v1 = *reinterpret_cast<const ulonglong2*>(vp + k * WW_TP + 4);
+      const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      const f32x2 v[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const f32x2 uu = pack2(u[c], u[c]);
+#pragma unroll
+        for (int tq = 0; tq < 4; ++tq) acc2[c][tq] = fma2(uu, v[tq], acc2[c][tq]);
+      }
+    }
+  };
+
+  const bool gemm_first = (warp & 4) != 0;
+  float pin[8], pg[4];
+  gather(s0, pin, pg);
+  scatter(0, pin, pg);
+  __syncthreads();   // staging buffer 0 visible
+  if (nk > 1) gather(s0 + 1, pin, pg);
+  transform(0, 0);
+  if (nk > 1) scatter(1, pin, pg);
+  __syncthreads();   // transformed buffer 0, staging buffer 1 visible
+
+  for (int k = 0; k < nk; ++k) {
+    const int buf = k & 1;
+    const bool next = k + 1 < nk, next2 = k + 2 < nk;
+    if (next2) gather(s0 + k + 2, pin, pg);   // loads in flight during the arithmetic below
+    if (gemm_first) {
+      gemm(buf);
+      if (next) transform(buf ^ 1, buf ^ 1);
+    } else {
+      if (next) transform(buf ^ 1, buf ^ 1);
+      gemm(buf);
+    }
+    if (next2) scatter(buf, pin, pg);   // staging buffer `buf` was last read by transform(k) during step k-1
+    __syncthreads();
+  }
+
+  // epilogue: gather the 16 frequencies of every (co, ci) through shared memory, dW = G^T dU G, accumulate atomically
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int tq = 0; tq < 4; ++tq) {
+      float lo, hi;
+      unpack2(acc2[c][tq], lo, hi);
+      float* mp = M_s + (p * WW_CH + cg * 8 + c) * 33 + tg * 8 + 2 * tq;
+      mp[0] = lo, mp[1] = hi;
+    }
+  __syncthreads();
+  for (int q = tid; q < WW_CH * WW_CH; q += WN_THREADS) {
+    const int col = q >> 5, cil = q & 31;
+    const int co = co0 + col, ci = ci0 + cil;
+    if (co >= a.Cout || ci >= a.Cin) continue;
+    float m[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[i][j] = M_s[((i * 4 + j) * WW_CH + col) * 33 + cil];
+    float pr[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pr[0][j] = m[0][j] + 0.5f * (m[1][j] + m[2][j]);
+      pr[1][j] = 0.5f * (m[1][j] - m[2][j]);
+      pr[2][j] = 0.5f * (m[1][j] + m[2][j]) + m[3][j];
+    }
+    float* dst = a.gw + ((size_t)co * a.Cin + ci) * 9;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      atomicAdd(dst + i * 3 + 0, pr[i][0] + 0.5f * (pr[i][1] + pr[i][2]));
+      atomicAdd(dst + i * 3 + 1, 0.5f * (pr[i][1] - pr[i][2]));
+      atomicAdd(dst + i * 3 + 2, 0.5f * (pr[i][1] + pr[i][2]) + pr[i][3]);
+    }
+  }
+}
+
 // grad_bias[co] = sum over b, y, x of g; grid (Cout, chunks), one atomicAdd per CTA into the zeroed output
 __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __restrict__ g, float* __restrict__ gb, int B, int Cout,
                                                              int HW) {
@@ -1225,6 +1447,29 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
   }
   if (grad_weight) {
     DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));
+    static const bool no_wino_wgrad = getenv("DD_NO_WINO_WGRAD") != nullptr;
+    if (!no_wino_wgrad && use_winograd(d->ksize, Cin, d->Cout)) {
+      WinoWgradArgs ww;
+      memset(&ww, 0, sizeof(ww));
+      ww.vin = materialise_up(d, workspace, ws, st);
+      ww.g = g, ww.B = d->B, ww.H = d->H, ww.W = d->W, ww.Cin = Cin, ww.Cout = d->Cout, ww.gw = grad_weight;
+      ww.nbr = (d->H + 3) / 4, ww.nbc = (d->W + 7) / 8;
+      const int n_steps = d->B * ww.nbr * ww.nbc;
+      const int gx = (d->Cout + WW_CH - 1) / WW_CH, gy = (Cin + WW_CH - 1) / WW_CH;
+      static bool configured = false;
+      const size_t smem = WW_SMEM_FLOATS * sizeof(float);
+      if (!configured) {
+        DD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_wino_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+      }
+      int splits = (device_sms() * 2) / (gx * gy);   // one wave of the two resident CTAs per SM
+      splits = splits < 1 ? 1 : (splits > n_steps ? n_steps : splits);
+      ww.steps_per_split = (n_steps + splits - 1) / splits;
+      splits = (n_steps + ww.steps_per_split - 1) / ww.steps_per_split;
+      conv_wgrad_wino_kernel<<<dim3(gx, gy, splits), WN_THREADS, smem, st>>>(ww);
+      dd::count_launches(1);
+      DD_CHECK_CUDA(cudaGetLastError());
+    } else {
     WgradArgs wa;
     memset(&wa, 0, sizeof(wa));
     wa.vin = materialise_up(d, workspace, ws, st);
@@ -1250,6 +1495,7 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
   } while (0)
     if (d->ksize == 3) DD_WGRAD(3); else DD_WGRAD(1);
 #undef DD_WGRAD
+    }
   }
   if (grad_x0 || grad_x1) {
     const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
