@@ -19,6 +19,10 @@
 
 namespace dd {
 
+#ifndef DD_WINO_UNROLL
+#define DD_WINO_UNROLL 4   // K-loop unrolling of the Winograd GEMMs (operand double-buffering vs register pressure)
+#endif
+constexpr int WINO_UNROLL = DD_WINO_UNROLL;
 constexpr int CT_H = 8, CT_W = 16;
 constexpr int CI_T = 8;
 constexpr int IN_PITCH = 20;
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
   auto gemm = [&](int buf) {
     const float* up = U_s + buf * 16 * CI_T * WN_CO + p * CI_T * WN_CO + cg * 8;
     const float* vp = V_s + buf * 16 * CI_T * WN_VP + p * CI_T * WN_VP + tg * 8;
-#pragma unroll 2
+#pragma unroll WINO_UNROLL
     for (int ci = 0; ci < CI_T; ++ci) {
       const float4 u0 = *reinterpret_cast<const float4*>(up + ci * WN_CO), u1 = *reinterpret_cast<const float4*>(up + ci * WN_CO + 4);
       const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP), v1 = *reinterpret_cast<const ulonglong2*>(vp + ci * WN_VP + 4);
@@ -1129,7 +1133,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
   auto gemm = [&](int buf) {
     const float* up = D_s + buf * 16 * WW_KT * WW_TP + p * WW_KT * WW_TP + cg * 8;
     const float* vp = V_s + buf * 16 * WW_KT * WW_TP + p * WW_KT * WW_TP + tg * 8;
-#pragma unroll 2
+#pragma unroll WINO_UNROLL
     for (int k = 0; k < WW_KT; ++k) {
       const float4 u0 = *reinterpret_cast<const float4*>(up + k * WW_TP), u1 = *reinterpret_cast<const float4*>(up + k * WW_TP + 4);
       const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(vp + k * WW_TP), v1 = *reinterpret_cast<const ulonglong2*>(vp + k * WW_TP + 4);

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdynamo_b200.so")
+# DD_B200_LIB selects another build of the same library (kernel A/B experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("DD_B200_LIB") or os.path.join(HERE, "libdynamo_b200.so")
 
 DD_MAX_SCALES = 4
 DD_MAX_FRAMES = 2
