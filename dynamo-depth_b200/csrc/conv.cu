@@ -507,8 +507,10 @@ constexpr int WN_THREADS = 256;
 constexpr int WN_CO = 32;
 constexpr int WN_TILES = 32;
 constexpr int WN_VP = 36;    // V_s pitch over tiles
-constexpr int WN_MP = 33;    // M_s pitch over tiles
-constexpr int WN_SMEM_LOOP = 2 * CI_T * IN_PLANE + 2 * 16 * CI_T * WN_VP + 2 * 16 * CI_T * WN_CO;
+constexpr int WN_MP = 32;    // M_s pitch over tiles (columns XOR-swizzled by the channel group: conflict-free 64-bit stores)
+constexpr int WN_IN_PITCH = 24;   // rows 2*ttr of the 4 tile rows land in disjoint 128-byte halves: conflict-free 64-bit transform loads
+constexpr int WN_IN_PLANE = (CT_H + 2) * WN_IN_PITCH + 4;   // 244
+constexpr int WN_SMEM_LOOP = 2 * CI_T * WN_IN_PLANE + 2 * 16 * CI_T * WN_VP + 2 * 16 * CI_T * WN_CO;
 constexpr int WN_SMEM_EPI = 16 * WN_CO * WN_MP;
 constexpr int WN_SMEM_FLOATS = WN_SMEM_LOOP > WN_SMEM_EPI ? WN_SMEM_LOOP : WN_SMEM_EPI;
 
@@ -531,8 +533,8 @@ __device__ __forceinline__ void emit_output(const ConvArgs& a, int b, int co, in
 __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int ROWS = CT_H + 2, COLS = CT_W + 2, NPOS = ROWS * COLS;
   extern __shared__ __align__(16) float wsm[];
-  float* in_s = wsm;                                  // [2][CI_T*IN_PLANE]
-  float* V_s = wsm + 2 * CI_T * IN_PLANE;             // [2][16][CI_T][WN_VP], transformed one step ahead
+  float* in_s = wsm;                                  // [2][CI_T*WN_IN_PLANE]
+  float* V_s = wsm + 2 * CI_T * WN_IN_PLANE;             // [2][16][CI_T][WN_VP], transformed one step ahead
   float* U_s = V_s + 2 * 16 * CI_T * WN_VP;           // [2][16][CI_T][WN_CO], filled by cp.async one step ahead
   float* M_s = wsm;                                   // epilogue only: [16][WN_CO][WN_MP]
 
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
   const int lr = tid / COLS, lc = tid - lr * COLS;
   build_tile_map(a.vin, ty0 + lr - 1 + a.oy, tx0 + lc - 1 + a.ox, te, o1);
   if (!has_pos) te.o00 = -1, o1 = -1;
-  const int s_off = has_pos ? lr * IN_PITCH + lc : 0;
+  const int s_off = has_pos ? lr * WN_IN_PITCH + lc : 0;
   const int C0 = a.vin.C0, Cin = a.Cin;
   const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win;
   const bool ok0 = te.o00 >= 0, ok1 = o1 >= 0;
@@ -587,9 +589,9 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
   };
   auto scatter = [&](int buf, const float (&pre)[CI_T]) {
     if (has_pos) {
-      float* dst = in_s + buf * CI_T * IN_PLANE + s_off;
+      float* dst = in_s + buf * CI_T * WN_IN_PLANE + s_off;
 #pragma unroll
-      for (int ci = 0; ci < CI_T; ++ci) dst[ci * IN_PLANE] = pre[ci];
+      for (int ci = 0; ci < CI_T; ++ci) dst[ci * WN_IN_PLANE] = pre[ci];
     }
   };
 
@@ -608,12 +610,12 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
 
   // input transform V = B^T d B of (channel ti, tile tt): in_s[ib] -> V_s[vb]
   auto transform = [&](int ib, int vb) {
-    const float* dp = in_s + ib * CI_T * IN_PLANE + ti * IN_PLANE + (2 * ttr) * IN_PITCH + 2 * ttc;
+    const float* dp = in_s + ib * CI_T * WN_IN_PLANE + ti * WN_IN_PLANE + (2 * ttr) * WN_IN_PITCH + 2 * ttc;
     float d[4][4], t[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 lo = *reinterpret_cast<const float2*>(dp + i * IN_PITCH);
-      const float2 hi = *reinterpret_cast<const float2*>(dp + i * IN_PITCH + 2);
+      const float2 lo = *reinterpret_cast<const float2*>(dp + i * WN_IN_PITCH);
+      const float2 hi = *reinterpret_cast<const float2*>(dp + i * WN_IN_PITCH + 2);
       d[i][0] = lo.x, d[i][1] = lo.y, d[i][2] = hi.x, d[i][3] = hi.y;
     }
 #pragma unroll
@@ -692,8 +694,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
     for (int tq = 0; tq < 4; ++tq) {
       float lo, hi;
       unpack2(acc2[c][tq], lo, hi);
-      float* mp = M_s + (p * WN_CO + cg * 8 + c) * WN_MP + tg * 8 + 2 * tq;
-      mp[0] = lo, mp[1] = hi;
+      *reinterpret_cast<float2*>(M_s + (p * WN_CO + cg * 8 + c) * WN_MP + ((tg * 8 + 2 * tq) ^ (2 * cg))) = make_float2(lo, hi);
     }
   __syncthreads();
   for (int q = tid; q < WN_CO * WN_TILES; q += WN_THREADS) {
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_c
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) m[i][j] = M_s[((i * 4 + j) * WN_CO + col) * WN_MP + tl];
+      for (int j = 0; j < 4; ++j) m[i][j] = M_s[((i * 4 + j) * WN_CO + col) * WN_MP + (tl ^ (2 * ((col >> 3) & 3)))];
     float sr[2][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1000,11 +1001,11 @@ constexpr int WW_CH = 32;                      // channels per CTA on either sid
 constexpr int WW_KT = 8;                       // tiles per K-step: 2 tile rows x 4 tile columns
 constexpr int WW_IN_R = 6, WW_IN_C = 10;       // input patch of a step (4x8 outputs + halo)
 constexpr int WW_IN_PITCH = 12;
-constexpr int WW_IN_PLANE = WW_IN_R * WW_IN_PITCH + 4;   // 76
-constexpr int WW_G_PLANE = 36;                 // 4x8 gradient block (+4)
+constexpr int WW_IN_PLANE = WW_IN_R * WW_IN_PITCH + 8;   // 80: two channels of a half-warp land in disjoint 64-byte quarters (conflict-free 64-bit transform loads)
+constexpr int WW_G_PLANE = 40;                 // 4x8 gradient block (+8, same reason)
 constexpr int WW_TP = 36;                      // pitch over channels of the transformed operands
 constexpr int WW_SMEM_LOOP = 2 * WW_CH * WW_IN_PLANE + 2 * WW_CH * WW_G_PLANE + 2 * 2 * 16 * WW_KT * WW_TP;
-constexpr int WW_SMEM_EPI = 16 * WW_CH * 33;
+constexpr int WW_SMEM_EPI = 16 * WW_CH * 32;
 constexpr int WW_SMEM_FLOATS = WW_SMEM_LOOP > WW_SMEM_EPI ? WW_SMEM_LOOP : WW_SMEM_EPI;
 
 struct WinoWgradArgs {
@@ -1022,7 +1023,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
   float* g_s = in_s + 2 * WW_CH * WW_IN_PLANE;         // [2][32 co][WW_G_PLANE]
   float* V_s = g_s + 2 * WW_CH * WW_G_PLANE;           // [2][16][8 tiles][WW_TP]  transformed input (ci inner)
   float* D_s = V_s + 2 * 16 * WW_KT * WW_TP;           // [2][16][8 tiles][WW_TP]  transformed output gradient (co inner)
-  float* M_s = wsm;                                    // epilogue: [16][32 co][33]
+  float* M_s = wsm;                                    // epilogue: [16][32 co][32 ci], columns XOR-swizzled by the co group
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int co0 = blockIdx.x * WW_CH, ci0 = blockIdx.y * WW_CH;
@@ -1180,8 +1181,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
     for (int tq = 0; tq < 4; ++tq) {
       float lo, hi;
       unpack2(acc2[c][tq], lo, hi);
-      float* mp = M_s + (p * WW_CH + cg * 8 + c) * 33 + tg * 8 + 2 * tq;
-      mp[0] = lo, mp[1] = hi;
+      *reinterpret_cast<float2*>(M_s + (p * WW_CH + cg * 8 + c) * 32 + ((tg * 8 + 2 * tq) ^ (2 * cg))) = make_float2(lo, hi);
     }
   __syncthreads();
   for (int q = tid; q < WW_CH * WW_CH; q += WN_THREADS) {
@@ -1192,7 +1192,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) m[i][j] = M_s[((i * 4 + j) * WW_CH + col) * 33 + cil];
+      for (int j = 0; j < 4; ++j) m[i][j] = M_s[((i * 4 + j) * WW_CH + col) * 32 + (cil ^ (2 * ((col >> 3) & 3)))];
     float pr[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
