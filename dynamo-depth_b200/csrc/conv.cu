@@ -1051,9 +1051,14 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc2[c][t] = 0ull;
 
-  auto gather = [&](int s, float (&pin)[8], float (&pg)[4]) {
-    const int b = s / per_img, rem = s - b * per_img;
-    const int br = rem / a.nbc, bc = rem - br * a.nbc;
+  // K-steps are visited in order: (image, block row, block column) of the next step to gather advance incrementally
+  int nb = s0 / per_img, nbr_i = (s0 - nb * per_img) / a.nbc, nbc_i = (s0 - nb * per_img) - nbr_i * a.nbc;
+  auto gather = [&](float (&pin)[8], float (&pg)[4]) {
+    const int b = nb, br = nbr_i, bc = nbc_i;
+    if (++nbc_i == a.nbc) {
+      nbc_i = 0;
+      if (++nbr_i == a.nbr) nbr_i = 0, ++nb;
+    }
     TapEntry te;
     int o1;
     build_tile_map(a.vin, 4 * br + ir - 1, 8 * bc + ic - 1, te, o1);
@@ -1151,10 +1156,10 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
 
   const bool gemm_first = (warp & 4) != 0;
   float pin[8], pg[4];
-  gather(s0, pin, pg);
+  gather(pin, pg);
   scatter(0, pin, pg);
   __syncthreads();   // staging buffer 0 visible
-  if (nk > 1) gather(s0 + 1, pin, pg);
+  if (nk > 1) gather(pin, pg);
   transform(0, 0);
   if (nk > 1) scatter(1, pin, pg);
   __syncthreads();   // transformed buffer 0, staging buffer 1 visible
@@ -1162,7 +1167,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
   for (int k = 0; k < nk; ++k) {
     const int buf = k & 1;
     const bool next = k + 1 < nk, next2 = k + 2 < nk;
-    if (next2) gather(s0 + k + 2, pin, pg);   // loads in flight during the arithmetic below
+    if (next2) gather(pin, pg);   // loads in flight during the arithmetic below
     if (gemm_first) {
       gemm(buf);
       if (next) transform(buf ^ 1, buf ^ 1);
