@@ -50,6 +50,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=8)
     a = ap.parse_args()
+    run("baseline fine_tune (warm-up run)", a.steps)
     run("baseline fine_tune", a.steps)
     run("lite-mono encoder channels_last", a.steps, channels_last=True)
     run("scoped tf32 lite-mono linear layers", a.steps, tf32=True)

@@ -174,21 +174,10 @@ class CDilated(nn.Module):
         return self.conv(x)
 
 
-def _mlp_residual(block, x, y_nhwc):
-    """x + drop_path(gamma * MLP(y)) with MLP = Linear(dim->6dim) - GELU - Linear(6dim->dim) on channels-last y
-    (reference: depth_encoder.py:196-220, 256-276).  Layer scale, the per-sample stochastic-depth factor and the
-    residual add run as ONE addcmul over the (strided) channels-last result instead of three element-wise passes;
-    the Bernoulli draw is the one DropPath.forward makes (same shape, same generator state)."""
-    z = block.pwconv2(block.act(block.pwconv1(y_nhwc))).permute(0, 3, 1, 2)
-    scale = block.gamma.view(1, -1, 1, 1) if block.gamma is not None else None
-    dp = block.drop_path
-    if isinstance(dp, DropPath) and dp.drop_prob > 0.0 and dp.training:
-        keep = 1.0 - dp.drop_prob
-        mask = x.new_empty((x.shape[0], 1, 1, 1)).bernoulli_(keep)
-        if keep > 0.0:
-            mask.div_(keep)
-        scale = mask if scale is None else scale * mask
-    return x + z if scale is None else torch.addcmul(x, z, scale)
+def _mlp_branch(block, x):
+    """shared inverted-bottleneck tail: Linear(dim->6dim) - GELU - Linear(6dim->dim) - layer scale."""
+    x = block.pwconv2(block.act(block.pwconv1(x)))
+    return block.gamma * x if block.gamma is not None else x
 
 
 class DilatedConv(nn.Module):
@@ -206,7 +195,9 @@ class DilatedConv(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
-        return _mlp_residual(self, x, self.bn1(self.ddwconv(x)).permute(0, 2, 3, 1))
+        y = self.bn1(self.ddwconv(x)).permute(0, 2, 3, 1)
+        y = _mlp_branch(self, y).permute(0, 3, 1, 2)
+        return x + self.drop_path(y)
 
 
 class LGFI(nn.Module):
@@ -233,7 +224,8 @@ class LGFI(nn.Module):
         if self.pos_embd is not None:
             t = t + self.pos_embd(B, H, W).reshape(B, -1, t.shape[1]).permute(0, 2, 1)
         t = t + self.gamma_xca * self.xca(self.norm_xca(t))
-        return _mlp_residual(self, x, self.norm(t.reshape(B, H, W, C)))
+        y = _mlp_branch(self, self.norm(t.reshape(B, H, W, C))).permute(0, 3, 1, 2)
+        return x + self.drop_path(y)
 
 
 class AvgPool(nn.Module):
