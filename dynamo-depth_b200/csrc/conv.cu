@@ -1015,6 +1015,7 @@ struct WinoWgradArgs {
   int nbr, nbc;          // 4x8 pixel blocks per image (rows, columns)
   int steps_per_split;
   float* gw;
+  float* gb;             // optional (Cout,) bias gradient, zero-initialised: summed by the first input-channel block
 };
 
 __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __grid_constant__ WinoWgradArgs a) {
@@ -1050,6 +1051,8 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc2[c][t] = 0ull;
+  const bool want_bias = a.gb != nullptr && blockIdx.y == 0;   // bias gradient rides on the transform of channel tc
+  float bias_acc = 0.f;
 
   // K-steps are visited in order: (image, block row, block column) of the next step to gather advance incrementally
   int nb = s0 / per_img, nbr_i = (s0 - nb * per_img) / a.nbc, nbc_i = (s0 - nb * per_img) - nbr_i * a.nbc;
@@ -1125,6 +1128,7 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
     {
       const float* gp = g_s + sb * WW_CH * WW_G_PLANE + tc * WW_G_PLANE + (2 * ttr) * 8 + 2 * ttc;
       const float2 y0 = *reinterpret_cast<const float2*>(gp), y1 = *reinterpret_cast<const float2*>(gp + 8);
+      if (want_bias) bias_acc += (y0.x + y0.y) + (y1.x + y1.y);   // every output pixel belongs to exactly one tile
       const float r[4][2] = {{y0.x, y0.y}, {y0.x + y1.x, y0.y + y1.y}, {y0.x - y1.x, y0.y - y1.y}, {-y1.x, -y1.y}};
       float* dp = D_s + tb * 16 * WW_KT * WW_TP + tt * WW_TP + tc;
 #pragma unroll
@@ -1179,6 +1183,12 @@ __global__ void __launch_bounds__(WN_THREADS, 2) conv_wgrad_wino_kernel(const __
     __syncthreads();
   }
 
+  if (want_bias) {   // threads tid = 8*tc + tt: sum the 8 tile lanes of each output channel
+    bias_acc += __shfl_xor_sync(0xffffffffu, bias_acc, 1);
+    bias_acc += __shfl_xor_sync(0xffffffffu, bias_acc, 2);
+    bias_acc += __shfl_xor_sync(0xffffffffu, bias_acc, 4);
+    if (tt == 0 && co0 + tc < a.Cout) atomicAdd(a.gb + co0 + tc, bias_acc);
+  }
   // epilogue: gather the 16 frequencies of every (co, ci) through shared memory, dW = G^T dU G, accumulate atomically
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -1445,8 +1455,10 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     conv_act_grad_kernel<<<(int)((n_out + 255) / 256 < 2368 ? (n_out + 255) / 256 : 2368), 256, 0, st>>>(grad_out, out, gc, n_out, d->act); dd::count_launches(1);
     g = gc;
   }
-  if (grad_bias) {
-    DD_CHECK_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d->Cout * sizeof(float), st));
+  static const bool no_wino_wgrad = getenv("DD_NO_WINO_WGRAD") != nullptr;
+  const bool wino_wgrad = grad_weight && !no_wino_wgrad && use_winograd(d->ksize, Cin, d->Cout);
+  if (grad_bias) DD_CHECK_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d->Cout * sizeof(float), st));
+  if (grad_bias && !wino_wgrad) {   // (the Winograd weight-gradient kernel sums the bias gradient on the way)
     const size_t total = (size_t)d->B * d->H * d->W;
     int chunks = (int)((total + 256 * 8 - 1) / (256 * 8));              // >= 8 elements per thread
     const int cap = (148 * 8 + d->Cout - 1) / d->Cout;                   // ~8 CTAs per SM over all channels
@@ -1456,12 +1468,11 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
   }
   if (grad_weight) {
     DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));
-    static const bool no_wino_wgrad = getenv("DD_NO_WINO_WGRAD") != nullptr;
-    if (!no_wino_wgrad && use_winograd(d->ksize, Cin, d->Cout)) {
+    if (wino_wgrad) {
       WinoWgradArgs ww;
       memset(&ww, 0, sizeof(ww));
       ww.vin = materialise_up(d, workspace, ws, st);
-      ww.g = g, ww.B = d->B, ww.H = d->H, ww.W = d->W, ww.Cin = Cin, ww.Cout = d->Cout, ww.gw = grad_weight;
+      ww.g = g, ww.B = d->B, ww.H = d->H, ww.W = d->W, ww.Cin = Cin, ww.Cout = d->Cout, ww.gw = grad_weight, ww.gb = grad_bias;
       ww.nbr = (d->H + 3) / 4, ww.nbc = (d->W + 7) / 8;
       const int n_steps = d->B * ww.nbr * ww.nbc;
       const int gx = (d->Cout + WW_CH - 1) / WW_CH, gy = (Cin + WW_CH - 1) / WW_CH;
