@@ -232,18 +232,24 @@ def run_ours(args):
     ms_e2e, _, _ = timed(pinned, args.steps, True)
     h2d = sum(v.numel() * v.element_size() for v in {id(v): v for v in pinned[0].values()}.values())
 
-    # opt-in variant (not the headline): Lite-Mono linear layers on the TF32 tensor cores (--encoder_tf32_linear)
+    # variants (not the headline): the Lite-Mono linear layers through torch's fp32 SIMT matmul (the previous default)
+    # and through cuBLAS single-pass TF32 (--encoder_tf32_linear, reduced precision) instead of the tcgen05 3xTF32 kernel
     variants = None
     if not args.no_variants:
         from networks.depth_encoder import EncoderLinear
-        EncoderLinear.tf32 = True
-        timed(resident, 2, False)
-        ms_v, _, _ = timed(resident, max(3, args.steps // 2), False)
-        EncoderLinear.tf32 = False
         v_steps = max(3, args.steps // 2)
-        variants = {"encoder_linear_tf32": {"value": world * BATCH * v_steps / (ms_v / 1000), "unit": UNIT, "ms_per_step": ms_v / v_steps,
-                                            "steps": v_steps, "note": "options --encoder_tf32_linear: the Lite-Mono encoder's nn.Linear "
-                                            "contractions in TF32 (scoped; everything else as in `value`); default keeps torch's fp32 matmul"}}
+        variants = {}
+        for name, (tf32, mode), note in (
+                ("encoder_linear_torch_fp32", (False, "torch"), "options --encoder_linear torch: the Lite-Mono encoder's nn.Linear "
+                 "contractions through torch's fp32 matmul (cuBLAS SIMT) instead of csrc/linear_tc.cu"),
+                ("encoder_linear_tf32", (True, "tc3x"), "options --encoder_tf32_linear: the same contractions in single-pass TF32 "
+                 "(cuBLAS, reduced precision; not parity-grade)")):
+            EncoderLinear.tf32, EncoderLinear.mode = tf32, mode
+            timed(resident, 2, False)
+            ms_v, _, _ = timed(resident, v_steps, False)
+            variants[name] = {"value": world * BATCH * v_steps / (ms_v / 1000), "unit": UNIT, "ms_per_step": ms_v / v_steps,
+                              "steps": v_steps, "note": note}
+        EncoderLinear.tf32, EncoderLinear.mode = False, "tc3x"
 
     if rank != 0:
         if world > 1:
@@ -289,7 +295,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args.phase), "global_batch": world * BATCH, "parallelism": f"dp{world}",
                        "l2": "per-step working set (>= 141 MB of colour frames plus GBs of activations) exceeds the 126 MB L2; no flush needed",
-                       "encoders": "PyTorch/cuDNN (TF32 convolutions = torch default, fp32 linear layers, channels_last ResNets); decoders + loss path: hand-written fp32 kernels",
+                       "encoders": "PyTorch/cuDNN convolutions (TF32 = torch default, channels_last ResNets); Lite-Mono linear layers: hand-written tcgen05 3xTF32 kernel (fp32 accuracy, csrc/linear_tc.cu); decoders + loss path: hand-written fp32 kernels",
                        "d_ground": "reference RANSAC prior kept on (host-driven torch ops, SURVEY 8f-1)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -120,6 +120,8 @@ SIGNATURES = {
     "dd_pose_matrix_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, FP, FP]),
     "dd_pose_matrix_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, FP, FP, FP]),
     "dd_ground_score": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, FP, FP]),
+    "dd_linear_fwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_linear_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP]),
 }
 
 _lib = None

@@ -671,3 +671,42 @@ def pose_matrix(axisangle, translation, invert):
     """(B,1,3) axis-angle / translation -> (B,4,4) (transformation_from_parameters)."""
     B = axisangle.shape[0]
     return _PoseMatrixFn.apply(_prep(axisangle.reshape(B, 3)), _prep(translation.reshape(B, 3)), bool(invert))
+
+
+class _LinearFn(torch.autograd.Function):
+    """F.linear on the tcgen05 tensor cores at fp32 accuracy (dd_linear_fwd / dd_linear_bwd, csrc/linear_tc.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = _prep(x).reshape(-1, x.shape[-1])
+        w = _prep(weight)
+        b = _prep(bias)
+        M, K = x2.shape
+        N = w.shape[0]
+        y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        with _timed("linear_fwd"):
+            L.check(L.load().dd_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), M, K, N, L.ptr(y), _stream()), "dd_linear_fwd")
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        return y.reshape(x.shape[:-1] + (N,))
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        g2 = _prep(g).reshape(M, N)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        gx = torch.empty((M, K), device=g.device, dtype=torch.float32) if need_x else None
+        gw = torch.empty((N, K), device=g.device, dtype=torch.float32) if (need_w or need_b) else None
+        gb = torch.empty((N,), device=g.device, dtype=torch.float32) if need_b else None
+        with _timed("linear_bwd"):
+            L.check(L.load().dd_linear_bwd(L.ptr(x2), L.ptr(w), L.ptr(g2), M, K, N, L.ptr(gx), L.ptr(gw), L.ptr(gb), _stream()),
+                    "dd_linear_bwd")
+        return (gx.reshape(ctx.x_shape) if need_x else None), (gw if need_w else None), gb
+
+
+def linear(x, weight, bias=None):
+    """y = x @ weight.T + bias over the last dimension of x (any leading shape); CUDA fp32 only."""
+    return _LinearFn.apply(x, weight, bias)

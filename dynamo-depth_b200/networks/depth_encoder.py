@@ -64,14 +64,22 @@ class _LinearTF32(torch.autograd.Function):
 
 
 class EncoderLinear(nn.Linear):
-    """nn.Linear of the encoder (same parameters / state_dict keys).  `tf32 = True` (opt-in, options
-    --encoder_tf32_linear) runs its contractions on the tensor cores in TF32 like every cuDNN convolution of the
-    reference already does under torch defaults; the default stays fp32 (torch's default for matmul)."""
+    """nn.Linear of the encoder (same parameters / state_dict keys; reference networks/depth_encoder.py:58-60,
+    :197-199, :243-245).  On CUDA the three contractions (forward, input gradient, weight gradient + bias gradient)
+    run in the hand-written tcgen05 kernel of csrc/linear_tc.cu: 3xTF32 operand split with fp32 accumulation in TMEM,
+    i.e. fp32 accuracy on the tensor cores (dd_b200.functional.linear).  `tf32 = True` (opt-in, options
+    --encoder_tf32_linear) uses cuBLAS single-pass TF32 instead, `mode = "torch"` (options --encoder_linear torch)
+    torch's fp32 SIMT matmul.  CPU tensors (oracle-side tests) always take F.linear."""
     tf32 = False
+    mode = "tc3x"
 
     def forward(self, x):
-        if EncoderLinear.tf32 and x.is_cuda:
-            return _LinearTF32.apply(x, self.weight, self.bias)
+        if x.is_cuda:
+            if EncoderLinear.tf32:
+                return _LinearTF32.apply(x, self.weight, self.bias)
+            if EncoderLinear.mode == "tc3x":
+                from dd_b200 import functional as DF
+                return DF.linear(x, self.weight, self.bias)
         return F.linear(x, self.weight, self.bias)
 
 

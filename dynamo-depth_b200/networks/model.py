@@ -43,9 +43,11 @@ class Model(nn.Module):
         # opt-in: skip the depth passes on frames -1/+1, which no loss term consumes.
         # Off by default because it changes BatchNorm running statistics / the DropPath RNG stream.
         self.skip_unused_depth = bool(getattr(options, "skip_unused_depth", False))
-        # opt-in: the Lite-Mono encoder's linear layers on the TF32 tensor cores (default fp32, torch's matmul default)
+        # Lite-Mono encoder linear layers: hand-written tcgen05 3xTF32 kernel (default, fp32 accuracy), torch fp32 SIMT, or
+        # (opt-in) cuBLAS single-pass TF32
         from . import depth_encoder as _de
         _de.EncoderLinear.tf32 = bool(getattr(options, "encoder_tf32_linear", False))
+        _de.EncoderLinear.mode = getattr(options, "encoder_linear", "tc3x")
 
     def forward(self, inputs):
         outputs = {}

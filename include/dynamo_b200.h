@@ -257,6 +257,20 @@ int dd_pose_matrix_bwd(const float* axisangle, const float* translation, const f
 int dd_ground_score(const float* points /* (B,3,H,W) */, const float* w /* (K,3), K = B*max_it */, int B, int H, int W,
                     int row0, int K, float tol, int32_t* counts /* (K) overwritten */, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Lite-Mono encoder linear layers (nn.Linear at networks/depth_encoder.py:58-60 XCA qkv / proj, :197-199 and
+ * :243-245 pwconv1 / pwconv2; called at :65,81,211-213,267-269) on the tcgen05 tensor cores at fp32 accuracy
+ * (3xTF32 operand split, fp32 accumulation in TMEM; csrc/linear_tc.cu).  Row-major fp32, 16-byte aligned pointers,
+ * K % 4 == 0, N % 4 == 0.
+ *   dd_linear_fwd: y (M,N) = x (M,K) . w (N,K)^T + bias (N) [bias may be NULL]
+ *   dd_linear_bwd: grad_x (M,K) = grad_y . w;  grad_w (N,K) = grad_y^T . x;  grad_b (N) = column sums of grad_y.
+ *                  Each output may be NULL (grad_b needs grad_w: it is summed by the weight-gradient pass); all
+ *                  are overwritten.
+ * ------------------------------------------------------------------------------------------ */
+int dd_linear_fwd(const float* x, const float* w, const float* bias, int M, int K, int N, float* y, void* stream);
+int dd_linear_bwd(const float* x, const float* w, const float* grad_y, int M, int K, int N, float* grad_x, float* grad_w,
+                  float* grad_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
