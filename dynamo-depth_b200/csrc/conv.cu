@@ -528,6 +528,12 @@ __device__ __forceinline__ void emit_output(const ConvArgs& a, int b, int co, in
   outp[o] = v;
 }
 
+}  // namespace dd
+
+#include "conv_tc.cuh"   // tcgen05 implicit-GEMM core (uses ConvArgs, build_tile_map, emit_output from above)
+
+namespace dd {
+
 // x0 arrives either as is or nearest-up-sampled (one tap per element); bilinear up-sampling is materialised by the host
 // wrapper (materialise_up) before the launch.
 __global__ void __launch_bounds__(WN_THREADS, 2) conv_wino_kernel(const __grid_constant__ ConvArgs a) {
@@ -1320,6 +1326,8 @@ static bool use_winograd(int ks, int cin, int cout) {
 
 static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose,
                     cudaStream_t st) {
+  if (use_tc_conv(ks, args.Cin, args.Cout))   // tensor cores (3xTF32): every layer with more than 16 output channels
+    return run_conv_tc(args, ks, wt_buf, w_oihw, Cout_f, Cin_f, transpose, device_sms(), st);
   if (use_winograd(ks, args.Cin, args.Cout)) {
     args.cout_pad = round_up(args.Cout, WN_CO);
     const size_t wn = (size_t)args.Cin * args.cout_pad;
@@ -1404,8 +1412,9 @@ static ConvWs conv_ws(const dd_conv_desc* d) {
   ConvWs w;
   const int KK = d->ksize * d->ksize;
   const int Cin = d->C0 + d->C1;
-  const size_t wt_f = (size_t)Cin * (KK == 9 ? 16 : KK) * round_up(d->Cout, 32) * sizeof(float);   // covers the Winograd layout
-  const size_t wt_d = (size_t)d->Cout * (KK == 9 ? 16 : KK) * round_up(Cin, 32) * sizeof(float);
+  // prepared weights: the largest of the Winograd layout [16][Cin][cout_pad] and the tensor-core layout [Cout][KK][cin_pad]
+  const size_t wt_f = (size_t)round_up(Cin, 32) * (KK == 9 ? 16 : KK) * round_up(d->Cout, 32) * sizeof(float);
+  const size_t wt_d = wt_f;
   const bool reflect = d->ksize == 3 && d->pad_mode == DD_PAD_REFLECT;
   const size_t Hp = d->H + (reflect ? 2 : 0), Wp = d->W + (reflect ? 2 : 0);
   w.wt = 0;

@@ -120,6 +120,10 @@ SIGNATURES = {
     "dd_pose_matrix_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, FP, FP]),
     "dd_pose_matrix_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, FP, FP, FP]),
     "dd_ground_score": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, FP, FP]),
+    "dd_nchw_to_nhwc": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_nhwc_to_nchw": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_block_tail_fwd": (C.c_int, [FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_block_tail_bwd": (C.c_int, [FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
     "dd_linear_fwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_linear_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP]),
 }

@@ -710,3 +710,64 @@ class _LinearFn(torch.autograd.Function):
 def linear(x, weight, bias=None):
     """y = x @ weight.T + bias over the last dimension of x (any leading shape); CUDA fp32 only."""
     return _LinearFn.apply(x, weight, bias)
+
+
+class _ToNHWCFn(torch.autograd.Function):
+    """(B,C,H,W) -> contiguous (B,H,W,C) (dd_nchw_to_nhwc); the gradient is the inverse transpose."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _prep(x)
+        B, C, H, W = x.shape
+        out = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        L.check(L.load().dd_nchw_to_nhwc(L.ptr(x), B, C, H * W, L.ptr(out), _stream()), "dd_nchw_to_nhwc")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _prep(g)
+        B, H, W, C = g.shape
+        gx = torch.empty((B, C, H, W), device=g.device, dtype=torch.float32)
+        L.check(L.load().dd_nhwc_to_nchw(L.ptr(g), B, C, H * W, L.ptr(gx), _stream()), "dd_nhwc_to_nchw")
+        return gx
+
+
+def nchw_to_nhwc(x):
+    """x.permute(0, 2, 3, 1).contiguous() as one tiled transpose (and one for its gradient)."""
+    return _ToNHWCFn.apply(x)
+
+
+class _BlockTailFn(torch.autograd.Function):
+    """out (B,C,H,W) = x + scale[b] * gamma[c] * y (B,H,W,C): layer scale + stochastic depth + residual of a Lite-Mono block."""
+
+    @staticmethod
+    def forward(ctx, x, y, gamma, scale):
+        x, y, gamma, scale = _prep(x), _prep(y), _prep(gamma), _prep(scale)
+        B, C, H, W = x.shape
+        if tuple(y.shape) != (B, H, W, C):
+            raise L.DynamoB200Error(f"block_tail: y {tuple(y.shape)} does not match x {tuple(x.shape)}")
+        out = torch.empty_like(x)
+        L.check(L.load().dd_block_tail_fwd(L.ptr(x), L.ptr(y), L.ptr(gamma), L.ptr(scale), B, C, H * W, L.ptr(out), _stream()),
+                "dd_block_tail_fwd")
+        ctx.save_for_backward(y, gamma, scale)
+        ctx.dims = (B, C, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, gamma, scale = ctx.saved_tensors
+        B, C, H, W = ctx.dims
+        g = _prep(g)
+        need_y = ctx.needs_input_grad[1]
+        need_gamma = gamma is not None and ctx.needs_input_grad[2]
+        gy = torch.empty_like(y) if need_y else None
+        gg = torch.empty_like(gamma) if need_gamma else None
+        if need_y or need_gamma:
+            L.check(L.load().dd_block_tail_bwd(L.ptr(g), L.ptr(y), L.ptr(gamma), L.ptr(scale), B, C, H * W, L.ptr(gy), L.ptr(gg),
+                                               _stream()), "dd_block_tail_bwd")
+        return (g if ctx.needs_input_grad[0] else None), gy, gg, None
+
+
+def block_tail(x, y, gamma=None, scale=None):
+    """x + (scale[:, None, None, None] * gamma * y).permute(0, 3, 1, 2) with y in (B,H,W,C); scale is not differentiated."""
+    return _BlockTailFn.apply(x, y, gamma, scale)

@@ -24,14 +24,19 @@ class DropPath(nn.Module):
         super().__init__()
         self.drop_prob = float(drop_prob)
 
-    def forward(self, x):
+    def sample(self, x):
+        """The per-sample factor Bernoulli(keep) / keep in the shape (B, 1, ..) (one RNG draw of B numbers), or None."""
         if self.drop_prob == 0.0 or not self.training:
-            return x
+            return None
         keep = 1.0 - self.drop_prob
         mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
         if keep > 0.0:
             mask.div_(keep)
-        return x * mask
+        return mask
+
+    def forward(self, x):
+        mask = self.sample(x)
+        return x if mask is None else x * mask
 
 
 class _LinearTF32(torch.autograd.Function):
@@ -188,6 +193,19 @@ def _mlp_branch(block, x):
     return block.gamma * x if block.gamma is not None else x
 
 
+def _fused(x):
+    """CUDA tensors take the hand-written layout-glue kernels (csrc/lite_glue.cu) unless EncoderLinear.mode == "torch"."""
+    return x.is_cuda and EncoderLinear.mode != "torch"
+
+
+def _block_tail(block, x, y):
+    """x + drop_path(gamma * y).permute(0, 3, 1, 2) for y in (B,H,W,C) as one kernel; the stochastic-depth factor is drawn
+    exactly like DropPath.forward draws it (same shape, same RNG stream)."""
+    from dd_b200 import functional as DF
+    scale = block.drop_path.sample(x) if isinstance(block.drop_path, DropPath) else None
+    return DF.block_tail(x, y, block.gamma, None if scale is None else scale.reshape(-1))
+
+
 class DilatedConv(nn.Module):
     """One block of the consecutive-dilated-convolution module: depth-wise dilated 3x3, BN, MLP, residual."""
 
@@ -203,6 +221,10 @@ class DilatedConv(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x):
+        if _fused(x):
+            from dd_b200 import functional as DF
+            y = DF.nchw_to_nhwc(self.bn1(self.ddwconv(x)))
+            return _block_tail(self, x, self.pwconv2(self.act(self.pwconv1(y))))
         y = self.bn1(self.ddwconv(x)).permute(0, 2, 3, 1)
         y = _mlp_branch(self, y).permute(0, 3, 1, 2)
         return x + self.drop_path(y)
@@ -228,10 +250,18 @@ class LGFI(nn.Module):
 
     def forward(self, x):
         B, C, H, W = x.shape
-        t = x.reshape(B, C, H * W).permute(0, 2, 1)
+        fused = _fused(x)
+        if fused:
+            from dd_b200 import functional as DF
+            t = DF.nchw_to_nhwc(x).reshape(B, H * W, C)
+        else:
+            t = x.reshape(B, C, H * W).permute(0, 2, 1)
         if self.pos_embd is not None:
             t = t + self.pos_embd(B, H, W).reshape(B, -1, t.shape[1]).permute(0, 2, 1)
         t = t + self.gamma_xca * self.xca(self.norm_xca(t))
+        if fused:
+            y = self.norm(t.reshape(B, H, W, C))
+            return _block_tail(self, x, self.pwconv2(self.act(self.pwconv1(y))))
         y = _mlp_branch(self, self.norm(t.reshape(B, H, W, C))).permute(0, 3, 1, 2)
         return x + self.drop_path(y)
 

@@ -271,6 +271,25 @@ int dd_linear_fwd(const float* x, const float* w, const float* bias, int M, int 
 int dd_linear_bwd(const float* x, const float* w, const float* grad_y, int M, int K, int N, float* grad_x, float* grad_w,
                   float* grad_b, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Layout glue of the Lite-Mono blocks (networks/depth_encoder.py:204-221 DilatedConv.forward, :252-279 LGFI.forward;
+ * csrc/lite_glue.cu): tiled transposes instead of PyTorch's strided element-wise kernels.
+ *   dd_nchw_to_nhwc : out (B,HW,C) = x (B,C,HW) transposed  -- `x.permute(0, 2, 3, 1)` made contiguous (:210, :256)
+ *   dd_nhwc_to_nchw : the inverse (its gradient)
+ *   dd_block_tail_fwd : out (B,C,HW) = x (B,C,HW) + scale[b] * gamma[c] * y (B,HW,C)  -- layer scale, stochastic
+ *                       depth (timm DropPath factor per sample) and residual add of :214-219 / :272-277;
+ *                       gamma and scale may be NULL (= 1)
+ *   dd_block_tail_bwd : grad_y (B,HW,C) = scale[b] * gamma[c] * grad_out (B,C,HW);
+ *                       grad_gamma[c] = sum_{b,p} scale[b] * grad_out[b,c,p] * y[b,p,c]   (either may be NULL;
+ *                       the gradient w.r.t. x is grad_out itself)
+ * ------------------------------------------------------------------------------------------ */
+int dd_nchw_to_nhwc(const float* x, int B, int C, int HW, float* out, void* stream);
+int dd_nhwc_to_nchw(const float* x, int B, int C, int HW, float* out, void* stream);
+int dd_block_tail_fwd(const float* x, const float* y, const float* gamma, const float* scale, int B, int C, int HW, float* out,
+                      void* stream);
+int dd_block_tail_bwd(const float* grad_out, const float* y, const float* gamma, const float* scale, int B, int C, int HW,
+                      float* grad_y, float* grad_gamma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

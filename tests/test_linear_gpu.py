@@ -66,12 +66,47 @@ def test_linear_rejects_cpu_and_bad_shapes():
         linear(torch.randn(8, 6, device="cuda"), torch.randn(8, 6, device="cuda"))
 
 
-@pytest.mark.parametrize("train", [False, True])
-def test_litemono_encoder_tc3x_matches_torch_fp32(train):
-    """Same weights, same input: encoder features and parameter gradients through the tcgen05 kernel vs torch fp32."""
+@pytest.mark.parametrize("B,C,HW", [(2, 64, 7680), (3, 224, 480), (2, 40, 100), (1, 7, 33)])
+def test_layout_glue_kernels(B, C, HW):
+    """dd_nchw_to_nhwc / dd_block_tail_* (csrc/lite_glue.cu) against the reference's permute / scale / add formulation."""
+    from dd_b200.functional import block_tail, nchw_to_nhwc
+    torch.manual_seed(B * 100 + C)
+    H, W = (HW // 20, 20) if HW % 20 == 0 else (1, HW)
+    x = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    y = torch.randn(B, H, W, C, device="cuda", requires_grad=True)
+    gamma = torch.randn(C, device="cuda", requires_grad=True)
+    scale = torch.tensor([0.0, 1.25, 1.25][:B], device="cuda")
+    go = torch.randn(B, C, H, W, device="cuda")
+    # transpose and its gradient
+    t = nchw_to_nhwc(x)
+    assert t.is_contiguous() and torch.equal(t, x.detach().permute(0, 2, 3, 1))
+    gt = torch.randn_like(t)
+    t.backward(gt)
+    assert torch.equal(x.grad, gt.permute(0, 3, 1, 2))
+    x.grad = None
+    for use_gamma, use_scale in ((True, True), (True, False), (False, False)):
+        x.grad = y.grad = gamma.grad = None
+        out = block_tail(x, y, gamma if use_gamma else None, scale if use_scale else None)
+        out.backward(go)
+        got = (out.detach(), x.grad.clone(), y.grad.clone(), gamma.grad.clone() if use_gamma else None)
+        x.grad = y.grad = gamma.grad = None
+        z = (gamma * y if use_gamma else y).permute(0, 3, 1, 2)
+        ref = x + (z * scale.view(-1, 1, 1, 1) if use_scale else z)
+        ref.backward(go)
+        assert torch.allclose(got[0], ref.detach(), rtol=1e-6, atol=1e-6)
+        assert torch.equal(got[1], x.grad)
+        assert torch.allclose(got[2], y.grad, rtol=1e-6, atol=1e-6)
+        if use_gamma:
+            assert _rel(got[3], gamma.grad.double()) < 1e-5
+
+
+@pytest.mark.parametrize("train,drop", [(False, 0.0), (True, 0.0), (True, 0.2)])
+def test_litemono_encoder_tc3x_matches_torch_fp32(train, drop):
+    """Same weights, same input, same RNG stream: encoder features and parameter gradients through the tcgen05 linear
+    kernel + layout-glue kernels vs the reference formulation in plain torch fp32."""
     from networks import depth_encoder as de
     torch.manual_seed(11)
-    enc = de.LiteMono(pretrained=False, drop_path_rate=0.0).cuda()
+    enc = de.LiteMono(pretrained=False, drop_path_rate=drop).cuda()
     enc.train(train)
     x = torch.rand(2, 3, 96, 160, device="cuda")
     res = {}
