@@ -49,18 +49,23 @@ __global__ void conv_prep_tc_weights_kernel(const float* __restrict__ w, float* 
   }
 }
 
+template <int NB32>
+__host__ __device__ constexpr int conv_tc_groups() { return tc::groups_for(tc::stages_for(2 * tc::A_TILE_BYTES + 2 * NB32 * 32 * tc::BK * 4)); }
+
 template <int KS, int NB32>
-__global__ void __launch_bounds__(tc::THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs g) {
+__global__ void __launch_bounds__(tc::cta_threads(conv_tc_groups<NB32>()), 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs g) {
   using namespace tc;
   constexpr int BN = NB32 * 32;
   constexpr int B_TILE_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int G = conv_tc_groups<NB32>();
+  constexpr int EPI_WARP0 = epi_warp0(G), MMA_WARP = mma_warp(G);
   constexpr int A_F4 = BM * BK / 4 / GROUP_THREADS;   // 8
   constexpr int B_F4 = BN * BK / 4 / GROUP_THREADS;   // 2 * NB32
   const ConvArgs& a = g.a;
 
   extern __shared__ uint8_t smem_raw[];
-  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES);
+  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES, MMA_WARP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.m_tiles * g.n_tiles;
   const int HoWo = a.Ho * a.Wo;
@@ -68,8 +73,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_tc_kernel(const __grid_co
   if (warp < EPI_WARP0) {
     // ------------------------------------------------------------------ producers
     const int grp = warp >> 2, ptid = threadIdx.x & (GROUP_THREADS - 1);
-    const int c4 = ptid & 31, kq = ptid >> 5;   // pixels 4*c4 .. 4*c4+3 of the tile; reduction steps kq, kq+4, ...
-    const uint32_t stages = (uint32_t)c.stages;
+    const int c4 = ptid & 31, kq = ptid >> 5;   // pixels 4*c4 .. 4*c4+3 of the tile; reduction steps kq, kq+4, ... (TileMap<true, 128>)
+    TileMap<true, BM> ma;
+    TileMap<false, BN> mb;
+    ma.init(ptid), mb.init(ptid);
+    const uint32_t stages = (uint32_t)c.stages, groups = G;
     const size_t plane0 = (size_t)a.vin.H0 * a.vin.W0, plane1 = (size_t)a.vin.Hin * a.vin.Win;
     const int C0 = a.vin.C0, Call = a.vin.C0 + a.vin.C1;
     const long long Ktot = (long long)KS * KS * g.cin_pad;
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_tc_kernel(const __grid_co
         base1[j] = a.vin.x1 + (size_t)b * a.vin.C1 * plane1;   // only dereferenced when C1 > 0
       }
       for (int kb = 0; kb < g.kb_total; ++kb, ++it) {
-        if ((int)(it & 1u) != grp) continue;
+        if ((int)(it % groups) != grp) continue;
         const uint32_t stage = it % stages, ph = (it / stages) & 1u;
         const int tap = kb / g.kb_per_tap, cb0 = (kb - tap * g.kb_per_tap) * BK;
         const int dy = KS == 3 ? tap / 3 - 1 : 0, dx = KS == 3 ? tap - (tap / 3) * 3 - 1 : 0;
@@ -116,12 +124,12 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_tc_kernel(const __grid_co
           }
           va[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        load_tile<false, BN, B_F4>(vb, a.wt, Ktot, nt * BN, a.Cout, kb * BK, (int)Ktot, ptid);
+        load_tile<false, BN, B_F4>(vb, mb, a.wt, Ktot, nt * BN, a.Cout, kb * BK, (int)Ktot);
         mbar_wait(c.empty_bar + 8 * stage, ph ^ 1u);
         const uint32_t a_hi = c.smem_base + stage * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
         const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-        store_tile<true, BM, A_F4>(va, a_hi, a_lo, ptid);    // chunk ptid + 128 i = (step kq + 4 i, pixels 4 c4 ..)
-        store_tile<false, BN, B_F4>(vb, b_hi, b_lo, ptid);
+        store_tile<true, BM, A_F4>(va, ma, a_hi, a_lo);    // chunk i = (step kq + 4 i, pixels 4 c4 ..)
+        store_tile<false, BN, B_F4>(vb, mb, b_hi, b_lo);
         fence_async_smem();
         mbar_arrive(c.full_bar + 8 * stage);
       }
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) conv_tc_kernel(const __grid_co
       mbar_arrive(c.tempty_bar + 8 * buf);
     }
   }
-  cta_teardown(c);
+  cta_teardown(c, MMA_WARP);
 }
 
 template <int KS, int NB32>
@@ -169,7 +177,7 @@ static int launch_conv_tc(ConvTcArgs& g, int sms, cudaStream_t st) {
   }
   const int total = g.m_tiles * g.n_tiles;
   // > half of the SM's shared memory in every configuration: one CTA per SM owns all 512 TMEM columns
-  conv_tc_kernel<KS, NB32><<<total < sms ? total : sms, tc::THREADS, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(g);
+  conv_tc_kernel<KS, NB32><<<total < sms ? total : sms, tc::cta_threads(conv_tc_groups<NB32>()), smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(g);
   dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;

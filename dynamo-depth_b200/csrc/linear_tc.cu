@@ -17,14 +17,15 @@
 // No transposed copies are made: the UMMA shared-memory descriptors take either major-ness, and both are filled by
 // the same coalesced 16-byte global loads.
 //
-// Structure (persistent CTAs, one per SM, 13 warps):
-//   warps 0-7   producers, two groups of 128 threads working on alternate K blocks: global fp32 -> registers ->
-//               (hi, lo) -> 128-byte-swizzled UMMA tiles in shared memory -> fence.proxy.async -> mbarrier `full`
-//   warp  12    one thread issues tcgen05.mma (M = 128, N = BN <= 256, K = 8 per instruction, 12 per K block of 32),
+// Structure (persistent CTAs, one per SM, 13 or 17 warps; building blocks in tc_common.cuh):
+//   producers   G = 3 groups (2 for tiles wider than 128 columns) of 128 threads working on K blocks it % G: global fp32 ->
+//               registers -> (hi, lo) -> 128-byte-swizzled UMMA tiles in shared memory -> fence.proxy.async -> mbarrier `full`
+//   MMA warp    one thread issues tcgen05.mma (M = 128, N = BN <= 256, K = 8 per instruction, 12 per K block of 32),
 //               tcgen05.commit releases the stage (`empty`) and hands the accumulator to the epilogue (`tmem_full`)
-//   warps 8-11  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> coalesced
+//   4 warps     epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> coalesced
 //               128-byte row segments (+ bias) or atomics; two accumulators in TMEM (2 x 256 columns) so the
 //               epilogue of tile i overlaps the MMAs of tile i+1
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -44,16 +45,21 @@ struct GemmArgs {
   int stages, atomic;
 };
 
+template <int NB32>
+__host__ __device__ constexpr int linear_groups() { return groups_for(stages_for(2 * A_TILE_BYTES + 2 * NB32 * 32 * BK * 4)); }
+
 template <bool A_MN, bool B_MN, int NB32>
-__global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_tc_kernel(const __grid_constant__ GemmArgs g) {
   constexpr int BN = NB32 * 32;
   constexpr int B_TILE_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int G = linear_groups<NB32>();
+  constexpr int EPI_WARP0 = epi_warp0(G), MMA_WARP = mma_warp(G);
   constexpr int A_F4 = BM * BK / 4 / GROUP_THREADS;   // 8
   constexpr int B_F4 = BN * BK / 4 / GROUP_THREADS;   // 2 * NB32
 
   extern __shared__ uint8_t smem_raw[];
-  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES);
+  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES, MMA_WARP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_mn = g.m_tiles * g.n_tiles;
   const int total_tiles = tiles_mn * g.splits;
@@ -61,32 +67,35 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const __grid_cons
   if (warp < EPI_WARP0) {
     // ------------------------------------------------------------------ producers
     const int grp = warp >> 2, ptid = threadIdx.x & (GROUP_THREADS - 1);
-    const uint32_t stages = (uint32_t)c.stages;
+    const uint32_t stages = (uint32_t)c.stages, groups = G;
+    TileMap<A_MN, BM> ma;
+    TileMap<B_MN, BN> mb;
+    ma.init(ptid), mb.init(ptid);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % g.n_tiles, r = tile / g.n_tiles, mt = r % g.m_tiles, sp = r / g.m_tiles;
       const int kb0 = sp * g.kb_per_split, kb1 = min(g.kb_total, kb0 + g.kb_per_split);
       float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        if ((int)(it & 1u) != grp) continue;
+        if ((int)(it % groups) != grp) continue;
         const uint32_t stage = it % stages, ph = (it / stages) & 1u;
         float4 va[A_F4], vb[B_F4];
-        load_tile<A_MN, BM, A_F4>(va, g.A, g.lda, mt * BM, g.Mc, kb * BK, g.Kr, ptid);
-        load_tile<B_MN, BN, B_F4>(vb, g.B, g.ldb, nt * BN, g.Nc, kb * BK, g.Kr, ptid);
-        if (A_MN) {   // bias gradient: a thread always holds the same four rows of A (GROUP_THREADS % (BM/4) == 0)
+        load_tile<A_MN, BM, A_F4>(va, ma, g.A, g.lda, mt * BM, g.Mc, kb * BK, g.Kr);
+        load_tile<B_MN, BN, B_F4>(vb, mb, g.B, g.ldb, nt * BN, g.Nc, kb * BK, g.Kr);
+        if (A_MN) {   // bias gradient: a thread always holds the same four rows of A (TileMap<true, 128>)
 #pragma unroll
           for (int i = 0; i < A_F4; ++i) cs.x += va[i].x, cs.y += va[i].y, cs.z += va[i].z, cs.w += va[i].w;
         }
         mbar_wait(c.empty_bar + 8 * stage, ph ^ 1u);
         const uint32_t a_hi = c.smem_base + stage * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
         const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-        store_tile<A_MN, BM, A_F4>(va, a_hi, a_lo, ptid);
-        store_tile<B_MN, BN, B_F4>(vb, b_hi, b_lo, ptid);
+        store_tile<A_MN, BM, A_F4>(va, ma, a_hi, a_lo);
+        store_tile<B_MN, BN, B_F4>(vb, mb, b_hi, b_lo);
         fence_async_smem();
         mbar_arrive(c.full_bar + 8 * stage);
       }
       if (A_MN && g.colsum != nullptr && nt == 0) {
-        const int row = mt * BM + (ptid & (BM / 4 - 1)) * 4;
+        const int row = mt * BM + ma.row_t;
         if (row < g.Mc) {   // Mc % 4 == 0
           atomicAdd(g.colsum + row, cs.x);
           atomicAdd(g.colsum + row + 1, cs.y);
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const __grid_cons
       mbar_arrive(c.tempty_bar + 8 * buf);   // accumulator drained: the MMA warp may overwrite it
     }
   }
-  cta_teardown(c);
+  cta_teardown(c, MMA_WARP);
 }
 
 template <bool A_MN, bool B_MN, int NB32>
@@ -159,7 +168,7 @@ int launch_one(const GemmArgs& g, int sm_count, cudaStream_t st) {
   }
   const int total = a.m_tiles * a.n_tiles * a.splits;
   const int grid = total < sm_count ? total : sm_count;
-  linear_tc_kernel<A_MN, B_MN, NB32><<<grid, THREADS, smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
+  linear_tc_kernel<A_MN, B_MN, NB32><<<grid, cta_threads(linear_groups<NB32>()), smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
   dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;

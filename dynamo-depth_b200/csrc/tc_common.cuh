@@ -3,11 +3,12 @@
 // instruction descriptors for tf32 operands of either major-ness, the fp32 -> (hi, lo) TF32 split, operand-tile
 // loaders, CTA set-up (barriers + TMEM allocation) and the single-thread MMA issue loop.
 //
-// CTA anatomy (one persistent CTA per SM, 13 warps): warps 0-7 = two producer groups of 128 threads working on
-// alternate K blocks (global fp32 -> registers -> hi/lo -> swizzled UMMA tiles -> fence.proxy.async -> `full`), warp 12 =
-// MMA issuer (one thread; tcgen05.commit -> `empty` / `tmem_full`), warps 8-11 = epilogue (tcgen05.ld of the TMEM lane
-// quarter warp % 4; `tmem_empty`); two accumulators (2 x 256 TMEM columns) overlap the epilogue of tile i with the MMAs of
-// tile i+1.
+// CTA anatomy (one persistent CTA per SM; G = 2 or 3 producer groups): warps 0..4G-1 = producer groups of 128 threads
+// working on K blocks it % G (global fp32 -> registers -> hi/lo -> swizzled UMMA tiles -> fence.proxy.async -> `full`), the
+// next four warps = epilogue (tcgen05.ld of the TMEM lane quarter warp % 4; `tmem_empty`), the last warp = MMA issuer (one
+// thread; tcgen05.commit -> `empty` / `tmem_full`); two accumulators (2 x 256 TMEM columns) overlap the epilogue of tile i with the MMAs of
+// tile i+1.  The producers are latency-bound (ncu: one instruction per ~10 clocks and warp, long-scoreboard + fixed-latency
+// stalls), so what matters is K blocks in flight (groups) and instructions per chunk (TileMap).
 #pragma once
 #include "dd_common.cuh"
 
@@ -17,9 +18,13 @@ namespace tc {
 constexpr int BM = 128;                  // UMMA M: rows of C per tile = TMEM lanes
 constexpr int BK = 32;                   // fp32 elements per K block = one 128-byte swizzle row
 constexpr int GROUP_THREADS = 128;       // one producer group
-constexpr int EPI_WARP0 = 8;
-constexpr int MMA_WARP = 12;
-constexpr int THREADS = 13 * 32;
+// Producer groups G work on K blocks it % G.  Parity waits on `empty` are only safe while a producer is at most one phase
+// behind the MMA warp; a group re-enters the ring after G K blocks, so G <= stages.  Wide tiles (BN > 128) have two stages
+// of shared memory -> two groups (13 warps, 128 registers per thread); narrower ones three (17 warps, 96 registers).
+__host__ __device__ constexpr int groups_for(int stages) { return stages >= 3 ? 3 : 2; }
+__host__ __device__ constexpr int epi_warp0(int groups) { return 4 * groups; }   // multiple of 4: epilogue warp w reads TMEM lane quarter w % 4
+__host__ __device__ constexpr int mma_warp(int groups) { return 4 * groups + 4; }
+__host__ __device__ constexpr int cta_threads(int groups) { return (4 * groups + 5) * 32; }
 constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int EPI_PITCH = 36;            // floats; 16-byte aligned rows, conflict-free 128-bit accesses
 constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
@@ -104,55 +109,66 @@ __device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, 
   st_shared_v4(lo_addr, v.x - hx, v.y - hy, v.z - hz, v.w - hw);
 }
 
-// Per-thread chunk c (of NF4) of an operand tile: where it comes from and where it goes.
-//   K-major : tile = ROWS x 32 floats, chunk f -> row f/8, 16-byte column f%8
-//   MN-major: tile = 32 reduction steps x ROWS, chunk f -> step f/(ROWS/4), rows 4*(f % (ROWS/4)) ..+3
+// Operand-tile geometry.  A producer thread moves NF4 16-byte chunks per tile; chunk i of thread t sits at
+// (row, reduction step) = (row_t + ROW_STEP * i', k_t + K_STEP * i'') with a shared-memory offset soff_t + constant(i):
+// everything that depends on the thread is derived once per kernel (init), everything that depends on i folds into
+// immediates of the unrolled loops -- per chunk the K loop issues one pointer add, one load, the hi/lo split and two stores.
+//   K-major  (tile ROWS x 32 floats)          : t -> row t/8 (+16 i), 16-byte column t%8          -> soff += 2048 i
+//   MN-major, ROWS == 128 (32 steps x 128 rows): t -> step t/32 (+4 i), rows 4 (t%32) ..           -> soff += 512 i
+//   MN-major, other ROWS                       : t -> step t/8 (+16 (i&1)), rows 32 (i>>1) + 4 (t%8) -> soff += 4096 (i>>1) + 2048 (i&1)
 template <bool MN, int ROWS>
 struct TileMap {
-  static constexpr int F4_PER_K = ROWS / 4;
-  __device__ static __forceinline__ void decode(int f, int& row, int& kk, uint32_t& soff) {
-    if (MN) {
-      kk = f / F4_PER_K;
-      const int c4 = f - kk * F4_PER_K;
-      row = c4 * 4;
-      soff = (uint32_t)((c4 >> 3) * 4096 + kk * 128 + (((((c4 & 7) >> 1) ^ (kk & 3)) << 5) | ((c4 & 1) << 4)));
+  static constexpr bool WIDE = MN && ROWS == 128;
+  int row_t, k_t;
+  uint32_t soff_t;
+  __device__ __forceinline__ void init(int ptid) {
+    if (!MN) {
+      row_t = ptid >> 3;
+      const int ch = ptid & 7;
+      k_t = ch * 4;
+      soff_t = (uint32_t)(row_t * 128 + ((ch ^ (row_t & 7)) << 4));
+    } else if (WIDE) {
+      const int c4 = ptid & 31;
+      k_t = ptid >> 5;
+      row_t = c4 * 4;
+      soff_t = (uint32_t)((c4 >> 3) * 4096 + k_t * 128 + (((((c4 & 7) >> 1) ^ (k_t & 3)) << 5) | ((c4 & 1) << 4)));
     } else {
-      row = f >> 3;
-      const int ch = f & 7;
-      kk = ch * 4;
-      soff = (uint32_t)(row * 128 + ((ch ^ (row & 7)) << 4));
+      const int c8 = ptid & 7;
+      k_t = ptid >> 3;
+      row_t = c8 * 4;
+      soff_t = (uint32_t)(k_t * 128 + ((((c8 >> 1) ^ (k_t & 3)) << 5) | ((c8 & 1) << 4)));
     }
+  }
+  __device__ static __forceinline__ constexpr int row_step(int i) { return !MN ? 16 * i : (WIDE ? 0 : 32 * (i >> 1)); }
+  __device__ static __forceinline__ constexpr int k_step(int i) { return !MN ? 0 : (WIDE ? 4 * i : 16 * (i & 1)); }
+  __device__ static __forceinline__ constexpr uint32_t s_step(int i) {
+    return !MN ? 2048u * i : (WIDE ? 512u * i : 4096u * (i >> 1) + 2048u * (i & 1));
   }
 };
 
+// rows [row0, ..) x reduction steps [k0, k0 + 32) of a row-major matrix -> registers (zeros outside rows_total x k_total)
 template <bool MN, int ROWS, int NF4>
-__device__ __forceinline__ void load_tile(float4 (&v)[NF4], const float* __restrict__ src, long long ld, int row0, int rows_total,
-                                          int k0, int k_total, int ptid) {
+__device__ __forceinline__ void load_tile(float4 (&v)[NF4], const TileMap<MN, ROWS>& m, const float* __restrict__ src, long long ld,
+                                          int row0, int rows_total, int k0, int k_total) {
+  const int gr0 = row0 + m.row_t, gk0 = k0 + m.k_t;
+  const float* p0 = MN ? src + (long long)gk0 * ld + gr0 : src + (long long)gr0 * ld + gk0;
 #pragma unroll
   for (int i = 0; i < NF4; ++i) {
-    int row, kk;
-    uint32_t soff;
-    TileMap<MN, ROWS>::decode(ptid + GROUP_THREADS * i, row, kk, soff);
-    const int gr = row0 + row, gk = k0 + kk;
+    const int rs = TileMap<MN, ROWS>::row_step(i), ks = TileMap<MN, ROWS>::k_step(i);
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gr < rows_total && gk < k_total) {
-      const float* p = MN ? src + (long long)gk * ld + gr : src + (long long)gr * ld + gk;
-      v[i] = __ldg(reinterpret_cast<const float4*>(p));
-    }
+    if (gr0 + rs < rows_total && gk0 + ks < k_total)
+      v[i] = __ldg(reinterpret_cast<const float4*>(MN ? p0 + (long long)ks * ld + rs : p0 + (long long)rs * ld + ks));
   }
 }
 
 template <bool MN, int ROWS, int NF4>
-__device__ __forceinline__ void store_tile(const float4 (&v)[NF4], uint32_t hi_base, uint32_t lo_base, int ptid) {
+__device__ __forceinline__ void store_tile(const float4 (&v)[NF4], const TileMap<MN, ROWS>& m, uint32_t hi_base, uint32_t lo_base) {
 #pragma unroll
   for (int i = 0; i < NF4; ++i) {
-    int row, kk;
-    uint32_t soff;
-    TileMap<MN, ROWS>::decode(ptid + GROUP_THREADS * i, row, kk, soff);
-    split_store(hi_base + soff, lo_base + soff, v[i]);
+    const uint32_t o = m.soff_t + TileMap<MN, ROWS>::s_step(i);
+    split_store(hi_base + o, lo_base + o, v[i]);
   }
 }
-
 
 // ---- CTA set-up ------------------------------------------------------------------------------------
 struct Cta {
@@ -171,7 +187,7 @@ __host__ __device__ constexpr int stages_for(int stage_bytes) {
                                                                                   : (SMEM_BUDGET - 1024 - EPI_BYTES - BAR_BYTES) / stage_bytes;
 }
 
-__device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stage_bytes) {
+__device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stage_bytes, int mma_warp_id) {
   Cta c;
   const uint32_t raw_addr = smem_u32(smem_raw);
   c.smem_base = (raw_addr + 1023u) & ~1023u;   // swizzle atoms are 1024-byte aligned
@@ -194,7 +210,7 @@ __device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stag
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == MMA_WARP) {
+  if (warp == mma_warp_id) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -205,10 +221,10 @@ __device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stag
   return c;
 }
 
-__device__ __forceinline__ void cta_teardown(const Cta& c) {
+__device__ __forceinline__ void cta_teardown(const Cta& c, int mma_warp_id) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == MMA_WARP) {
+  if ((threadIdx.x >> 5) == mma_warp_id) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem_base), "r"(TMEM_COLS) : "memory");
   }
