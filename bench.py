@@ -227,6 +227,20 @@ def run_ours(args):
     k_fwd = statistics.mean(a.elapsed_time(b) for a, b in kt.get("warp_photo_fwd", [])) if kt.get("warp_photo_fwd") else None
     k_bwd = statistics.mean(a.elapsed_time(b) for a, b in kt.get("warp_photo_bwd", [])) if kt.get("warp_photo_bwd") else None
 
+    # tensor-core linear kernel (csrc/linear_tc.cu): two extra, untimed-for-the-headline steps with per-call events
+    Fn.KERNEL_TIMERS = {"__detail__": True}
+    timed(resident, 2, False)
+    kt_lin = Fn.KERNEL_TIMERS
+    Fn.KERNEL_TIMERS = None
+    lin = {}
+    for key in ("linear_fwd", "linear_bwd"):
+        calls = kt_lin.get(key, [])
+        if calls:
+            ms_k = sum(a.elapsed_time(b) for a, b, _ in calls)
+            lin[key] = {"calls_per_step": len(calls) // 2, "ms_per_step": ms_k / 2,
+                        "tflops_fp32_equivalent": sum(m[0] for _, _, m in calls) / (ms_k * 1e-3) / 1e12,
+                        "algorithmic_gbs": sum(m[1] for _, _, m in calls) / (ms_k * 1e-3) / 1e9}
+
     # end-to-end: pinned host inputs copied every step + loss read back every step
     timed(pinned, 4, True)      # the copy stream's staging buffers reach their steady state (three batches in flight)
     ms_e2e, _, _ = timed(pinned, args.steps, True)
@@ -282,6 +296,14 @@ def run_ours(args):
                              "achieved": (bwd_bytes / (k_bwd * 1e-3) / 1e9) if k_bwd else None,
                              "frac": (bwd_bytes / (k_bwd * 1e-3) / 1e9 / peak) if k_bwd else None,
                              "traffic": traffic.get(f"warp_photo_bwd_{args.phase}")}}
+    if lin:
+        # the tensor-core kernel of the step (Lite-Mono linear layers, tcgen05 3xTF32): skinny GEMMs, so HBM is the bound;
+        # the tensor figure is fp32-equivalent work (each counted multiply-add costs three TF32 MMAs) against bf16_tflops / 6
+        tf_peak = peaks.get("bf16_tflops", 2250.0) / 2.0 / 3.0
+        roofline["tensor_kernel"] = {
+            "kernel": "linear_tc_kernel (dd_linear_fwd / dd_linear_bwd)", "bound": "hbm", "peak": peak, "unit": "GB/s",
+            "tensor_peak_tflops_3xtf32": tf_peak,
+            **{k: dict(v, frac=v["algorithmic_gbs"] / peak, tensor_frac=v["tflops_fp32_equivalent"] / tf_peak) for k, v in lin.items()}}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -96,17 +96,24 @@ __global__ void __launch_bounds__(tc::cta_threads(conv_tc_groups<NB32>()), 1) co
         base0[j] = a.vin.x0 + (size_t)b * C0 * plane0;
         base1[j] = a.vin.x1 + (size_t)b * a.vin.C1 * plane1;   // only dereferenced when C1 > 0
       }
+      int last_tap = -1;
+      const float* p0[4];
+      const float* p1[4];
       for (int kb = 0; kb < g.kb_total; ++kb, ++it) {
         if ((int)(it % groups) != grp) continue;
         const uint32_t stage = it % stages, ph = (it / stages) & 1u;
         const int tap = kb / g.kb_per_tap, cb0 = (kb - tap * g.kb_per_tap) * BK;
-        const int dy = KS == 3 ? tap / 3 - 1 : 0, dx = KS == 3 ? tap - (tap / 3) * 3 - 1 : 0;
-        int o0[4], o1[4];
+        if (tap != last_tap) {   // source positions of the four pixels for this tap (NULL = padding / outside)
+          last_tap = tap;
+          const int dy = KS == 3 ? tap / 3 - 1 : 0, dx = KS == 3 ? tap - (tap / 3) * 3 - 1 : 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          TapEntry e;
-          build_tile_map(a.vin, a.oy + py[j] + dy, a.ox + px[j] + dx, e, o1[j]);
-          o0[j] = e.o00;
+          for (int j = 0; j < 4; ++j) {
+            TapEntry e;
+            int o1;
+            build_tile_map(a.vin, a.oy + py[j] + dy, a.ox + px[j] + dx, e, o1);
+            p0[j] = e.o00 >= 0 ? base0[j] + e.o00 : nullptr;
+            p1[j] = (o1 >= 0 && a.vin.C1 > 0) ? base1[j] + o1 : nullptr;
+          }
         }
         float4 va[A_F4], vb[B_F4];
 #pragma unroll
@@ -114,13 +121,15 @@ __global__ void __launch_bounds__(tc::cta_threads(conv_tc_groups<NB32>()), 1) co
           const int ch = cb0 + kq + 4 * i;
           float v[4] = {0.f, 0.f, 0.f, 0.f};
           if (ch < C0) {
+            const size_t co = (size_t)ch * plane0;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (o0[j] >= 0) v[j] = __ldg(base0[j] + (size_t)ch * plane0 + o0[j]);
+              if (p0[j]) v[j] = __ldg(p0[j] + co);
           } else if (ch < Call) {
+            const size_t co = (size_t)(ch - C0) * plane1;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (o1[j] >= 0) v[j] = __ldg(base1[j] + (size_t)(ch - C0) * plane1 + o1[j]);
+              if (p1[j]) v[j] = __ldg(p1[j] + co);
           }
           va[i] = make_float4(v[0], v[1], v[2], v[3]);
         }

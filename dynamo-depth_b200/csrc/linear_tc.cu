@@ -211,9 +211,16 @@ int gemm(int mode, const float* A, long long lda, const float* B, long long ldb,
   memset(&g, 0, sizeof(g));
   g.A = A, g.B = B, g.C = C, g.bias = bias, g.colsum = colsum;
   g.lda = lda, g.ldb = ldb, g.ldc = ldc, g.Mc = Mc, g.Nc = Nc, g.Kr = Kr;
+  // N tile = 32 * nb32 columns: the narrowest of the widths 192 / 224 / 256 that wastes the fewest padded columns (a
+  // 192-wide tile measured 5-12 % faster than 224 / 256 at equal waste: lighter producers per K block); one tile when N <= 256
+  static const int forced_nb32 = getenv("DD_LINEAR_MAX_NB32") ? atoi(getenv("DD_LINEAR_MAX_NB32")) : 0;
   const int n32 = (Nc + 31) / 32;
-  g.n_tiles = (n32 + 7) / 8;
-  const int nb32 = (n32 + g.n_tiles - 1) / g.n_tiles;
+  int nb32 = 0, best_waste = 1 << 30;
+  for (int cap = forced_nb32 > 0 ? forced_nb32 : 6; cap <= (forced_nb32 > 0 ? forced_nb32 : 8); ++cap) {
+    const int tiles = (n32 + cap - 1) / cap, nb = (n32 + tiles - 1) / tiles;
+    const int waste = ((n32 + nb - 1) / nb) * nb - n32;
+    if (waste < best_waste) best_waste = waste, nb32 = nb;
+  }
   g.n_tiles = (n32 + nb32 - 1) / nb32;
   g.m_tiles = (Mc + BM - 1) / BM;
   g.kb_total = (Kr + BK - 1) / BK;

@@ -41,19 +41,23 @@ KERNEL_TIMERS = None
 
 
 class _timed:
-    def __init__(self, name):
-        self.name = name
+    """CUDA events around one C-ABI call while KERNEL_TIMERS is a dict.  `detail` timers (the many linear-layer calls of a
+    step) are only taken when KERNEL_TIMERS["__detail__"] is set, and carry `meta` (e.g. flops / bytes of the call)."""
+
+    def __init__(self, name, meta=None, detail=False):
+        self.name, self.meta, self.detail = name, meta, detail
+        self.ev = None
 
     def __enter__(self):
-        if KERNEL_TIMERS is not None:
+        if KERNEL_TIMERS is not None and (not self.detail or KERNEL_TIMERS.get("__detail__")):
             self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             self.ev[0].record()
         return self
 
     def __exit__(self, *exc):
-        if KERNEL_TIMERS is not None:
+        if self.ev is not None:
             self.ev[1].record()
-            KERNEL_TIMERS.setdefault(self.name, []).append(self.ev)
+            KERNEL_TIMERS.setdefault(self.name, []).append(self.ev if self.meta is None else self.ev + (self.meta,))
         return False
 
 
@@ -684,7 +688,7 @@ class _LinearFn(torch.autograd.Function):
         M, K = x2.shape
         N = w.shape[0]
         y = torch.empty((M, N), device=x.device, dtype=torch.float32)
-        with _timed("linear_fwd"):
+        with _timed("linear_fwd", meta=(2.0 * M * K * N, 4.0 * (M * K + N * K + M * N)), detail=True):
             L.check(L.load().dd_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), M, K, N, L.ptr(y), _stream()), "dd_linear_fwd")
         ctx.save_for_backward(x2, w)
         ctx.has_bias = bias is not None
@@ -701,7 +705,9 @@ class _LinearFn(torch.autograd.Function):
         gx = torch.empty((M, K), device=g.device, dtype=torch.float32) if need_x else None
         gw = torch.empty((N, K), device=g.device, dtype=torch.float32) if (need_w or need_b) else None
         gb = torch.empty((N,), device=g.device, dtype=torch.float32) if need_b else None
-        with _timed("linear_bwd"):
+        flops = 2.0 * M * K * N * (int(bool(need_x)) + int(gw is not None))
+        nbytes = 4.0 * ((M * N + N * K + M * K) * int(bool(need_x)) + (M * N + M * K + N * K) * int(gw is not None))
+        with _timed("linear_bwd", meta=(flops, nbytes), detail=True):
             L.check(L.load().dd_linear_bwd(L.ptr(x2), L.ptr(w), L.ptr(g2), M, K, N, L.ptr(gx), L.ptr(gw), L.ptr(gb), _stream()),
                     "dd_linear_bwd")
         return (gx.reshape(ctx.x_shape) if need_x else None), (gw if need_w else None), gb
