@@ -29,6 +29,7 @@ import torch.optim as optim
 
 import networks
 from dd_b200 import _lib as L
+from dd_b200 import checkpoint as ckpt
 from dd_b200 import functional as Fn
 from dd_b200.parallel import GradArena
 from tools import BackprojectDepth, DepthMetrics, GroundPlane, Project3D, SSIM, depth_to_disp, disp_to_depth
@@ -122,27 +123,46 @@ class Trainer:
         return {"optimizer": optimizer, "lr_scheduler": sched, "network_names": network_names}
 
     # ------------------------------------------------------------------ training loop
-    def train(self, loader_factory=None):
+    def train(self, loader_factory=None, resume_from=None):
         """loader_factory(trainer) -> iterable of `inputs` dicts for one epoch (the reference's dataset
-        classes are out of scope; dd_b200.synthetic.SyntheticTriplets is the built-in source)."""
+        classes are out of scope; dd_b200.synthetic.SyntheticTriplets is the built-in source).
+        resume_from (or options --resume): a `models/<phase>_<epoch>` folder written by save_model; the run continues
+        with the next epoch of that phase (weights, Adam moments, LR schedule, counters and RNG streams restored)."""
         if loader_factory is None:
             from dd_b200.synthetic import SyntheticTriplets
             loader_factory = lambda tr: SyntheticTriplets(tr.opt, steps=tr.num_steps_per_epoch, device=tr.device)
         self.loader_factory = loader_factory
         self.g_step = 0
-        for phase_i, phase_name in enumerate(["disp_init", "motion_init", "mask_init", "fine_tune"]):
+        resume_from = resume_from or getattr(self.opt, "resume", "")
+        first_phase, first_epoch, state = 0, 0, None
+        if resume_from:
+            state = ckpt.load_state(resume_from)
+            first_phase, first_epoch = ckpt.resume_point(state, self.opt.epoch_schedules)
+            self.opt.load_ckpt = resume_from
+            self.load_model()
+            self.base_model.to(self.device)
+            self.g_step = state["g_step"]
+            self.print(f"======== resuming after {state['phase_name']} epoch {state['epoch']} ({resume_from}) ========")
+        for phase_i, phase_name in enumerate(ckpt.PHASES):
             num_epoch = self.opt.epoch_schedules[phase_i]
+            if phase_i < first_phase:
+                continue
             self.print(f"======== {phase_name.upper()} - Num Epochs={num_epoch} ========")
             if num_epoch > 0:
-                self.run_phase(phase_name, num_epoch)
+                same_phase = state is not None and phase_name == state["phase_name"]
+                self.run_phase(phase_name, num_epoch, start_epoch=first_epoch if phase_i == first_phase else 0,
+                               state=state if same_phase else None)
 
-    def run_phase(self, phase_name, num_epoch):
+    def run_phase(self, phase_name, num_epoch, start_epoch=0, state=None):
         self.setup_phase(phase_name)
         self.step, self.epoch = 0, 0
+        if state is not None:          # continuing inside the phase the checkpoint was written in
+            ckpt.apply_state(state, self.optim["optimizer"], self.optim["lr_scheduler"])
+            self.step = state["step"]
         self.bool_automask = phase_name == "disp_init"
         self.num_total_steps = self.num_steps_per_epoch * num_epoch
         self.start_time = time.time()
-        for self.epoch in range(num_epoch):
+        for self.epoch in range(start_epoch, num_epoch):
             self.run_epoch(self.loader_factory(self))
             if ((self.epoch + 1) % self.opt.save_frequency == 0) or (self.epoch == num_epoch - 1):
                 self.save_model(phase_name)
@@ -393,7 +413,9 @@ class Trainer:
             return
         folder = join_dir(self.log_path, "models", f"{save_name}_{self.epoch:02}")
         self.base_model.save(folder)
-        torch.save(self.optim["optimizer"].state_dict(), osp.join(folder, "adam.pth"))
+        torch.save(self.optim["optimizer"].state_dict(), osp.join(folder, "adam.pth"))   # as the reference (Trainer.py:706-707)
+        ckpt.save_state(folder, ckpt.pack_state(self.phase_name, self.epoch, self.step, self.g_step, self.optim["optimizer"],
+                                                self.optim["lr_scheduler"], self.opt.epoch_schedules))
 
     def load_model(self):
         self.base_model.load(verbose=self.is_main())

@@ -74,6 +74,8 @@ _ARGS = [
     (("--encoder_tf32_linear",), dict(action="store_true")),   # Lite-Mono linear layers in single-pass TF32 (cuBLAS)
     # Lite-Mono linear layers: "tc3x" = tcgen05 3xTF32 kernel at fp32 accuracy (csrc/linear_tc.cu), "torch" = torch fp32 matmul
     (("--encoder_linear",), dict(type=str, default="tc3x", choices=["tc3x", "torch"])),
+    # continue an interrupted run: a models/<phase>_<epoch> folder written by Trainer.save_model (weights + trainer_state.pth)
+    (("--resume",), dict(type=str, default="")),
 ]
 
 # values filled in when the corresponding option is left at None (options.py:274-301)
