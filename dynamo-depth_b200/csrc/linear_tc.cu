@@ -4,8 +4,10 @@
 //
 // Accuracy: every fp32 operand x is split on the fly into hi = rn_tf32(x) and lo = x - hi (exact), and each K step
 // issues three MMAs  D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  with fp32 accumulation in TMEM ("3xTF32"): the dropped
-// A_lo*B_lo term and the hardware's truncation of lo to 10 mantissa bits are both <= 2^-21 relative per product, i.e.
-// the result is as close to the exact product as torch's fp32 SIMT GEMM (tests: 1e-5 relative against float64).
+// A_lo*B_lo term and the hardware's truncation of lo to 10 mantissa bits are both <= 2^-21 relative per product.
+// Measured against float64: 3e-7 .. 1.2e-5 of the output scale, growing with the reduction length (64 .. 1344; the
+// tensor core's fp32 accumulator truncates), where torch's fp32 SIMT GEMM measures 2e-7 .. 1e-6 -- an order of
+// magnitude inside the 1e-4 parity bound; tests/test_linear_gpu.py holds the kernel to 2e-5.
 //
 // One kernel, three contractions C (Mc x Nc) = A_op * B_op^T over a reduction of length Kr, selected by which operand
 // is "K-major" (reduction index contiguous in memory) or "MN-major" (row index contiguous):
