@@ -98,6 +98,30 @@ def test_cpu_tensors_are_refused_by_every_op():
         tools.BackprojectDepth(1, 8, 8)(torch.rand(1, 1, 8, 8), torch.eye(4)[None])
     with pytest.raises(DynamoB200Error):
         tools.compute_smooth_loss(x, x)
+    with pytest.raises(DynamoB200Error):
+        Fn.linear(torch.rand(8, 8), torch.rand(4, 8), torch.rand(4))
+    with pytest.raises(DynamoB200Error):
+        Fn.nchw_to_nhwc(x)
+    with pytest.raises(DynamoB200Error):
+        Fn.block_tail(x, x.permute(0, 2, 3, 1).contiguous(), torch.rand(3))
+
+
+def test_encoder_layers_keep_the_reference_formulation_on_cpu():
+    """The oracle-side tests run the product's Lite-Mono modules on the CPU: there EncoderLinear is F.linear and the
+    blocks use the reference's permute / layer-scale / DropPath / residual formulation (no kernel involved)."""
+    from networks import depth_encoder as de
+
+    torch.manual_seed(0)
+    blk = de.DilatedConv(dim=8, k=3, dilation=1, drop_path=0.5).train()
+    x = torch.rand(4, 8, 6, 10)
+    torch.manual_seed(1)
+    got = blk(x)
+    torch.manual_seed(1)
+    y = blk.bn1(blk.ddwconv(x)).permute(0, 2, 3, 1)
+    y = blk.gamma * torch.nn.functional.linear(blk.act(torch.nn.functional.linear(y, blk.pwconv1.weight, blk.pwconv1.bias)),
+                                                 blk.pwconv2.weight, blk.pwconv2.bias)
+    mask = x.new_empty(4, 1, 1, 1).bernoulli_(0.5).div_(0.5)
+    assert torch.allclose(got, x + y.permute(0, 3, 1, 2) * mask)
 
 
 def test_options_defaults_match_reference_surface():
