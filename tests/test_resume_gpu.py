@@ -46,6 +46,8 @@ def test_trainer_resume_continues_schedule(tmp_path):
     # same data (seeded synthetic triplets), same restored state: the resumed epoch lands close to the uninterrupted one
     a = torch.load(os.path.join(models, "disp_init_01", "depth_dec.pth"), map_location="cpu")
     b = torch.load(os.path.join(models2, "disp_init_01", "depth_dec.pth"), map_location="cpu")
-    moved = max(float((a[k] - w0[k]).abs().max()) for k in a)
-    apart = max(float((a[k] - b[k]).abs().max()) for k in a)
-    assert moved > 0 and apart <= 0.5 * moved, (moved, apart)
+    # (mean over all weights: Adam's sign-like update can flip on an isolated weight whose gradient is rounding noise)
+    n = sum(a[k].numel() for k in a)
+    moved = sum(float((a[k] - w0[k]).abs().sum()) for k in a) / n
+    apart = sum(float((a[k] - b[k]).abs().sum()) for k in a) / n
+    assert moved > 0 and apart <= 0.1 * moved, (moved, apart)
