@@ -72,12 +72,12 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 // Shared-memory matrix descriptor (tcgen05).  Addresses / offsets in 16-byte units.
 //   K-major  tile [row][32 fp32], SWIZZLE_128B (16-byte chunk ^= row % 8): 8-row groups 1024 B apart (SBO); LBO unused
 //   MN-major tile [row/32][k][32 fp32], SWIZZLE_128B_BASE32B -- the only MN-major layout of 32-bit operands (32-byte
-//            chunk ^= k % 4, atom = 4 reduction steps x 128 B): groups of 32 rows 4096 B apart (LBO), groups of 4
-//            reduction steps 512 B apart (SBO); one instruction (K = 8) covers two of them
+//            chunk ^= k % 4, atom = 4 reduction steps x 128 B): groups of 32 rows mn_group_bytes apart (LBO; 4096 for a
+//            32-step K block), groups of 4 reduction steps 512 B apart (SBO); one instruction (K = 8) covers two of them
 template <bool MN>
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t mn_group_bytes = 4096u) {
   uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
-  d |= (uint64_t)(MN ? (4096u >> 4) : 1u) << 16;
+  d |= (uint64_t)(MN ? (mn_group_bytes >> 4) : 1u) << 16;
   d |= (uint64_t)(MN ? (512u >> 4) : (1024u >> 4)) << 32;
   d |= (uint64_t)1 << 46;               // descriptor version (sm_100)
   d |= (uint64_t)(MN ? 1 : 2) << 61;    // SWIZZLE_128B_BASE32B : SWIZZLE_128B
@@ -187,7 +187,7 @@ __host__ __device__ constexpr int stages_for(int stage_bytes) {
                                                                                   : (SMEM_BUDGET - 1024 - EPI_BYTES - BAR_BYTES) / stage_bytes;
 }
 
-__device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stage_bytes, int mma_warp_id) {
+__device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stage_bytes, int mma_warp_id, int full_count = GROUP_THREADS) {
   Cta c;
   const uint32_t raw_addr = smem_u32(smem_raw);
   c.smem_base = (raw_addr + 1023u) & ~1023u;   // swizzle atoms are 1024-byte aligned
@@ -201,7 +201,7 @@ __device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stag
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(c.full_bar + 8 * s, GROUP_THREADS);
+      mbar_init(c.full_bar + 8 * s, full_count);
       mbar_init(c.empty_bar + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
