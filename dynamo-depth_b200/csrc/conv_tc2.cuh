@@ -1,7 +1,6 @@
-// EXPERIMENTAL (DD_TC_CONV=2) -- written at the end of round 1 after the GPU budget was spent: it compiles for sm_100a but
-// has NOT run on hardware yet; nothing selects it unless the environment variable is set.  First thing to do with it:
-// `DD_TC_CONV=2 python -m pytest tests/test_conv_gpu.py -m gpu` (every padding / up-sampling / concat / epilogue variant
-// against torch), then `DD_TC_CONV=2 python dev/kernel_bench.py --what conv`.
+// EXPERIMENTAL (DD_TC_CONV=2) -- written at the end of round 1 when the GPU budget was nearly spent.  Status: parity-green
+// on the B200 (all 26 tests of tests/test_conv_gpu.py pass with DD_TC_CONV=2), NOT yet timed; nothing selects it unless the
+// environment variable is set.  Next: `DD_TC_CONV=2 python dev/kernel_bench.py --what conv` against the Winograd numbers.
 //
 // 3x3 decoder convolutions (forward and data gradient of ConvBlock / Conv3x3, networks/layers.py:85-121) as implicit GEMMs
 // on the tcgen05 tensor cores (3xTF32, fp32 accuracy) WITHOUT the per-tap im2col gather of conv_tc.cuh, which keeps that
