@@ -1,6 +1,8 @@
 // EXPERIMENTAL (DD_TC_CONV=2) -- written at the end of round 1 when the GPU budget was nearly spent.  Status: parity-green
-// on the B200 (all 26 tests of tests/test_conv_gpu.py pass with DD_TC_CONV=2), NOT yet timed; nothing selects it unless the
-// environment variable is set.  Next: `DD_TC_CONV=2 python dev/kernel_bench.py --what conv` against the Winograd numbers.
+// on the B200 (all 26 tests of tests/test_conv_gpu.py pass with DD_TC_CONV=2); one 3-repetition timing puts it level with
+// the Winograd kernels on the >= 64-channel layers (0.77x .. 1.13x of their time) and behind on the 32-channel full-resolution
+// layer (1.7x): producer-bound (8-channel K blocks, two groups), see DESIGN.md section 6.  Nothing selects it unless the
+// environment variable is set.
 //
 // 3x3 decoder convolutions (forward and data gradient of ConvBlock / Conv3x3, networks/layers.py:85-121) as implicit GEMMs
 // on the tcgen05 tensor cores (3xTF32, fp32 accuracy) WITHOUT the per-tap im2col gather of conv_tc.cuh, which keeps that
