@@ -31,7 +31,7 @@ import networks
 from dd_b200 import _lib as L
 from dd_b200 import checkpoint as ckpt
 from dd_b200 import functional as Fn
-from dd_b200.parallel import GradArena
+from dd_b200.parallel import GradArena, broadcast_module_state
 from tools import BackprojectDepth, DepthMetrics, GroundPlane, Project3D, SSIM, depth_to_disp, disp_to_depth
 from utils import join_dir, sec_to_hm_str
 
@@ -62,6 +62,13 @@ class Trainer:
         self.base_model.to(self.device)
         self.model = self.base_model          # no DDP wrapper: gradients are reduced through the arena
         self.world_size = int(os.environ.get("WORLD_SIZE", 1)) if getattr(self.opt, "ddp", False) else 1
+        if self.world_size > 1:
+            # What the DDP constructor does in the reference (Trainer.py:44): every replica starts from rank 0's
+            # parameters and buffers, whatever the local seeds / initialisation order were.
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("opt.ddp is set with WORLD_SIZE > 1 but torch.distributed is not initialised (train.py does it)")
+            broadcast_module_state(self.base_model, src=0)
 
         self.num_scales = len(self.opt.scales)
         self.B, self.H, self.W = self.opt.batch_size, self.opt.height, self.opt.width
@@ -87,10 +94,15 @@ class Trainer:
         self.automask_noise = None           # {scale: (B,F,H,W)} to inject the tie-break noise (parity tests)
         self.freeze_inactive = True          # no backward through networks the current phase does not optimise
         self.step, self.epoch, self.g_step = 0, 0, 0
+        # steps per epoch drive the loss-weight ramp (Trainer.py:307-308); the reference takes len(train_loader)
+        # (Trainer.py:505), run_epoch does the same whenever the loader has a length
         self.num_steps_per_epoch = max(1, int(getattr(self.opt, "epoch_size", 1)))
         self.bool_automask = False
         self.arena = None
         self.optim = None
+        self.overlap_allreduce = True        # all-reduce arena chunks from autograd hooks while backward is still running
+        if self.is_main() and getattr(self.opt, "model_name", "--") != "--":
+            self.save_opt()                  # as the reference (Trainer.py:85)
 
     # ------------------------------------------------------------------ phases / optimiser
     def setup_phase(self, phase_name):
@@ -115,8 +127,13 @@ class Trainer:
         self.phase_name = phase_name
 
     def get_optim(self, network_names, optm=optim.Adam, lr_factor=1):
-        params = self.base_model.parameters_by_names(network_names)
-        self.arena = GradArena(params, world_size=self.world_size)
+        named = self.base_model.named_parameters_by_names(network_names)
+        params = [p for _, p in named]
+        if self.arena is not None:
+            self.arena.release()
+        self.arena = GradArena(params, world_size=self.world_size, names=[n for n, _ in named],
+                               chunk_ids=[n.split(".", 1)[0] for n, _ in named], overlap=self.overlap_allreduce)
+        self.param_names = self.arena.names
         kw = {"fused": True} if optm is optim.Adam else {}
         optimizer = optm(params, self.opt.learning_rate * lr_factor, **kw)
         sched = optim.lr_scheduler.StepLR(optimizer, self.opt.scheduler_step_size, 0.5)
@@ -143,6 +160,8 @@ class Trainer:
             self.base_model.to(self.device)
             self.g_step = state["g_step"]
             self.print(f"======== resuming after {state['phase_name']} epoch {state['epoch']} ({resume_from}) ========")
+        if state is not None:
+            ckpt.restore_rng_state(state)          # also when the checkpoint closed a phase and the next one starts fresh
         for phase_i, phase_name in enumerate(ckpt.PHASES):
             num_epoch = self.opt.epoch_schedules[phase_i]
             if phase_i < first_phase:
@@ -157,13 +176,19 @@ class Trainer:
         self.setup_phase(phase_name)
         self.step, self.epoch = 0, 0
         if state is not None:          # continuing inside the phase the checkpoint was written in
-            ckpt.apply_state(state, self.optim["optimizer"], self.optim["lr_scheduler"])
+            ckpt.apply_state(state, self.optim["optimizer"], self.optim["lr_scheduler"], param_names=self.param_names,
+                             restore_rng=False)
             self.step = state["step"]
         self.bool_automask = phase_name == "disp_init"
-        self.num_total_steps = self.num_steps_per_epoch * num_epoch
         self.start_time = time.time()
         for self.epoch in range(start_epoch, num_epoch):
-            self.run_epoch(self.loader_factory(self))
+            loader = self.loader_factory(self)
+            if hasattr(loader, "__len__"):
+                if len(loader) <= 0:
+                    raise ValueError("the loader of this epoch is empty")
+                self.num_steps_per_epoch = len(loader)     # Trainer.py:505
+            self.num_total_steps = self.num_steps_per_epoch * num_epoch
+            self.run_epoch(loader)
             if ((self.epoch + 1) % self.opt.save_frequency == 0) or (self.epoch == num_epoch - 1):
                 self.save_model(phase_name)
 
@@ -415,7 +440,8 @@ class Trainer:
         self.base_model.save(folder)
         torch.save(self.optim["optimizer"].state_dict(), osp.join(folder, "adam.pth"))   # as the reference (Trainer.py:706-707)
         ckpt.save_state(folder, ckpt.pack_state(self.phase_name, self.epoch, self.step, self.g_step, self.optim["optimizer"],
-                                                self.optim["lr_scheduler"], self.opt.epoch_schedules))
+                                                self.optim["lr_scheduler"], self.opt.epoch_schedules,
+                                                param_names=[(n, tuple(p.shape)) for n, p in zip(self.arena.names, self.arena.params)]))
 
     def load_model(self):
         self.base_model.load(verbose=self.is_main())

@@ -16,8 +16,10 @@ STATE_FILE = "trainer_state.pth"
 FORMAT_VERSION = 1
 
 
-def pack_state(phase_name, epoch, step, g_step, optimizer, lr_scheduler, epoch_schedules, with_rng=True):
-    """Everything needed to continue after `epoch` (0-based, completed) of `phase_name`."""
+def pack_state(phase_name, epoch, step, g_step, optimizer, lr_scheduler, epoch_schedules, with_rng=True, param_names=None):
+    """Everything needed to continue after `epoch` (0-based, completed) of `phase_name`.
+    param_names: [("<module>.<param>", shape), ...] in optimiser order -- Adam moments are stored by index, so the
+    resuming process must attach them to the same parameters (checked by apply_state)."""
     if phase_name not in PHASES:
         raise ValueError(f"unknown phase {phase_name!r}")
     state = {
@@ -26,6 +28,8 @@ def pack_state(phase_name, epoch, step, g_step, optimizer, lr_scheduler, epoch_s
         "epoch_schedules": [int(e) for e in epoch_schedules],
         "optimizer": optimizer.state_dict(), "lr_scheduler": lr_scheduler.state_dict(),
     }
+    if param_names is not None:
+        state["param_names"] = [(str(n), tuple(int(d) for d in shp)) for n, shp in param_names]
     if with_rng:
         rng = {"torch_cpu": torch.get_rng_state(), "numpy": np.random.get_state()}
         if torch.cuda.is_available():
@@ -49,19 +53,32 @@ def load_state(folder):
     return state
 
 
-def apply_state(state, optimizer, lr_scheduler, restore_rng=True):
-    """Load optimiser / scheduler (and RNG) state; the caller has already built them for state['phase_name']."""
+def restore_rng_state(state):
+    if "rng" in state:
+        torch.set_rng_state(state["rng"]["torch_cpu"])
+        np.random.set_state(state["rng"]["numpy"])
+        if "torch_cuda" in state["rng"] and torch.cuda.is_available():
+            torch.cuda.set_rng_state(state["rng"]["torch_cuda"])
+
+
+def apply_state(state, optimizer, lr_scheduler, restore_rng=True, param_names=None):
+    """Load optimiser / scheduler (and RNG) state; the caller has already built them for state['phase_name'].
+    param_names: this process's optimiser-order parameter names; compared with the checkpoint's record."""
+    if param_names is not None and "param_names" in state:
+        saved_names = [n for n, _ in state["param_names"]]
+        if list(param_names) != saved_names:
+            diff = next((i for i, (a, b) in enumerate(zip(param_names, saved_names)) if a != b), min(len(param_names), len(saved_names)))
+            raise ValueError(f"optimiser parameter order differs from the checkpoint's at index {diff}: "
+                             f"{param_names[diff] if diff < len(param_names) else None!r} vs "
+                             f"{saved_names[diff] if diff < len(saved_names) else None!r}")
     own, saved = optimizer.state_dict()["param_groups"], state["optimizer"]["param_groups"]
     if [len(g["params"]) for g in own] != [len(g["params"]) for g in saved]:
         raise ValueError("optimiser state does not match the phase's parameter list "
                          f"({[len(g['params']) for g in saved]} saved vs {[len(g['params']) for g in own]} now)")
     optimizer.load_state_dict(state["optimizer"])
     lr_scheduler.load_state_dict(state["lr_scheduler"])
-    if restore_rng and "rng" in state:
-        torch.set_rng_state(state["rng"]["torch_cpu"])
-        np.random.set_state(state["rng"]["numpy"])
-        if "torch_cuda" in state["rng"] and torch.cuda.is_available():
-            torch.cuda.set_rng_state(state["rng"]["torch_cuda"])
+    if restore_rng:
+        restore_rng_state(state)
 
 
 def resume_point(state, epoch_schedules):

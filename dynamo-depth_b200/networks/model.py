@@ -15,6 +15,9 @@ from .pose_decoder import PoseDecoder
 from .resnet_encoder import ResnetEncoder
 
 
+MODULE_ORDER = ("depth_enc", "depth_dec", "pose_enc", "pose_dec", "motion_enc", "motion_dec", "motion_mask")
+
+
 class Model(nn.Module):
     network2modules = None   # filled per instance (kept as an attribute like the reference)
 
@@ -37,12 +40,17 @@ class Model(nn.Module):
         self.motion_mask = MotionDecoder(self.pose_enc.num_ch_enc, self.opt.scales, num_input_images=3, inp_disp=False, out_dim=1)
         self.network2modules = {"Depth": ["depth_enc", "depth_dec"], "Pose": ["pose_enc", "pose_dec"],
                                 "CmpFlow": ["motion_enc", "motion_dec"], "MotMask": ["motion_enc", "motion_mask"]}
-        self.module_names = list(set(m for mods in self.network2modules.values() for m in mods))
+        # Fixed order (the reference's list(set(...)) depends on PYTHONHASHSEED): the gradient-arena layout, the Adam
+        # state order of a checkpoint and the construction-time broadcast must be identical in every process.
+        self.module_names = [m for m in MODULE_ORDER if any(m in mods for mods in self.network2modules.values())]
         self.bool_CmpFlow = True
         self.bool_MotMask = True
         # opt-in: skip the depth passes on frames -1/+1, which no loss term consumes.
         # Off by default because it changes BatchNorm running statistics / the DropPath RNG stream.
         self.skip_unused_depth = bool(getattr(options, "skip_unused_depth", False))
+        # opt-in: the two pose-encoder calls (reference model.py:82-86) as ONE batch of 2B image pairs.
+        # Off by default: the pose encoder's BatchNorm then normalises over both pairs together (train mode).
+        self.batch_pose_pairs = bool(getattr(options, "batch_pose_pairs", False))
         # Lite-Mono encoder linear layers: hand-written tcgen05 3xTF32 kernel (default, fp32 accuracy), torch fp32 SIMT, or
         # (opt-in) cuBLAS single-pass TF32
         from . import depth_encoder as _de
@@ -64,10 +72,22 @@ class Model(nn.Module):
                 outputs[(name, f, s)] = v
 
     def predict_poses(self, inputs, outputs):
-        for f in self.opt.frame_ids[1:]:
-            pair = torch.cat([inputs["color_aug", f, 0], inputs["color_aug", 0, 0]], 1)   # target frame always last
-            feats = self.pose_enc(pair)
-            axisangle, translation = self.pose_dec([feats])
+        frames = self.opt.frame_ids[1:]
+        pairs = [torch.cat([inputs["color_aug", f, 0], inputs["color_aug", 0, 0]], 1) for f in frames]   # target frame always last
+        batched = None
+        if self.batch_pose_pairs and len(frames) > 1:
+            B = pairs[0].shape[0]
+            feats_all = self.pose_enc(torch.cat(pairs, 0))
+            aa_all, tr_all = self.pose_dec([feats_all])
+            batched = [([ft[i * B:(i + 1) * B] for ft in feats_all], aa_all[i * B:(i + 1) * B], tr_all[i * B:(i + 1) * B])
+                       for i in range(len(frames))]
+        for i, f in enumerate(frames):
+            pair = pairs[i]
+            if batched is not None:
+                feats, axisangle, translation = batched[i]
+            else:
+                feats = self.pose_enc(pair)
+                axisangle, translation = self.pose_dec([feats])
             axisangle, translation = axisangle[:, 0], translation[:, 0]
             outputs[("pose_feats", 0, f)] = [pair] + feats
             outputs[("axisangle", 0, f)] = axisangle
@@ -98,12 +118,23 @@ class Model(nn.Module):
                     outputs[(name, prev, s)] = v
                     outputs[(name, nxt, s)] = v
 
+    def modules_by_names(self, network_names):
+        """Sub-module names of the given networks in the fixed MODULE_ORDER, each once (motion_enc is shared)."""
+        wanted = set(m for n in network_names for m in self.network2modules[n])
+        return [m for m in MODULE_ORDER if m in wanted]
+
     def parameters_by_names(self, network_names):
-        mods = list(set(m for n in network_names for m in self.network2modules[n]))
         params = []
-        for m in mods:
+        for m in self.modules_by_names(network_names):
             params += list(getattr(self, m).parameters())
         return params
+
+    def named_parameters_by_names(self, network_names):
+        """[("<module>.<param>", parameter)] in the order of parameters_by_names (layout check / checkpoints)."""
+        named = []
+        for m in self.modules_by_names(network_names):
+            named += [(f"{m}.{k}", p) for k, p in getattr(self, m).named_parameters()]
+        return named
 
     def save(self, save_folder):
         for name in self.module_names:

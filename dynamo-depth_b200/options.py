@@ -71,6 +71,7 @@ _ARGS = [
     (("--eval_img_type",), dict(type=str, choices=["original", "downsample"], default=None)),
     # B200 build only (not in the reference; defaults keep the reference's behaviour)
     (("--skip_unused_depth",), dict(action="store_true")),     # no depth passes on frames -1/+1 (no loss term reads them)
+    (("--batch_pose_pairs",), dict(action="store_true")),      # both pose-encoder calls as one batch of 2B pairs (changes BN batch statistics)
     (("--encoder_tf32_linear",), dict(action="store_true")),   # Lite-Mono linear layers in single-pass TF32 (cuBLAS)
     # Lite-Mono linear layers: "tc3x" = tcgen05 3xTF32 kernel at fp32 accuracy (csrc/linear_tc.cu), "torch" = torch fp32 matmul
     (("--encoder_linear",), dict(type=str, default="tc3x", choices=["tc3x", "torch"])),

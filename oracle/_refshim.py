@@ -17,7 +17,19 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("DD_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """$DD_REFERENCE_ROOT, else the read-only tree of the build container, else the unmodified install that
+    __graft_entry__.build() puts under baseline/_ref (git-ignored; the only copy that exists on the GPU box)."""
+    for cand in (os.environ.get("DD_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "Trainer.py")):
+            return cand
+    return os.environ.get("DD_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 class _DropPath(nn.Module):

@@ -23,3 +23,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _parity_case_name(request):
+    """Every comparison helper of oracle/compare.py logs its measured error under the running test's name."""
+    from oracle import compare
+
+    compare.CURRENT_CASE = request.node.name
+    yield
+    compare.CURRENT_CASE = "unnamed"

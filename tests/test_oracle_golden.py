@@ -64,3 +64,46 @@ def test_fp64_oracle_close_to_fp32_reference():
     case = LossCase("loss_maskinit_lite_32x64")
     outputs, leaves, losses = run_oracle(case, torch.float64)
     assert float(losses["loss"]) == pytest.approx(case.losses["loss"], rel=1e-4)
+
+
+# ---- stand-alone layers: oracle functions vs the reference's tools.py (tests/golden/tools_standalone.npz) ---------
+def _tools_golden():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tools_standalone.npz"))
+    return z, {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in:")}
+
+
+def _close(got, ref, rel=1e-5):
+    ref = torch.as_tensor(ref)
+    err = (got.detach() - ref).abs().max().item()
+    assert err <= rel * ref.abs().max().item() + 1e-12, (err, ref.abs().max().item())
+
+
+def test_standalone_oracle_layers_match_reference_tools():
+    z, d = _tools_golden()
+    B, _, H, W = d["depth"].shape
+    depth = d["depth"].clone().requires_grad_(True)
+    cam = vs.backproject(depth, d["inv_K"])
+    (cam * d["ct_cam"]).sum().backward()
+    _close(cam, z["backproject:out"]), _close(depth.grad, z["backproject:g_depth"])
+    for tag, T in (("project_T", d["T"]), ("project_noT", None)):
+        pts = cam.detach().clone().requires_grad_(True)
+        Tt = T.clone().requires_grad_(True) if T is not None else None
+        pix, ego = vs.project(pts, d["K"], Tt, H, W)
+        ((pix * d["ct_pix"]).sum() + (ego * d["ct_ego"]).sum()).backward()
+        _close(pix, z[f"{tag}:pix"]), _close(ego, z[f"{tag}:ego"], 2e-5), _close(pts.grad, z[f"{tag}:g_points"])
+        if Tt is not None:
+            _close(Tt.grad, z[f"{tag}:g_T"], 2e-5)
+    x, y = d["x"].clone().requires_grad_(True), d["y"].clone().requires_grad_(True)
+    s = vs.ssim(x, y)
+    (s * d["ct_ssim"]).sum().backward()
+    _close(s, z["ssim:out"], 2e-5), _close(x.grad, z["ssim:g_x"], 1e-4), _close(y.grad, z["ssim:g_y"], 1e-4)
+    for tag, inp, img in (("smooth1", d["smooth_inp1"], d["smooth_img"]), ("smooth3", d["smooth_inp3"], d["smooth_img"]),
+                          ("smooth_noimg", d["smooth_inp3"], None)):
+        t = inp.clone().requires_grad_(True)
+        v = vs.smooth_loss(t, img)
+        v.backward()
+        _close(v, z[f"{tag}:out"]), _close(t.grad, z[f"{tag}:g_inp"])
+    scaled, dep = vs.disp_to_depth(d["disp"], 0.1, 100.0)
+    _close(scaled, z["disp_to_depth:scaled"]), _close(dep, z["disp_to_depth:depth"])
+    _close(vs.depth_to_disp(dep, 0.1, 100.0), z["depth_to_disp:out"])

@@ -134,3 +134,135 @@ def test_options_defaults_match_reference_surface():
     assert (opt.height, opt.width, opt.scales, opt.split) == (192, 640, [0, 1, 2, 3], "eigen_zhou")
     g = sorted(k for k in vars(opt) if k.startswith("g_"))
     assert g == ["g_c_consistency", "g_c_smooth", "g_d_ground", "g_d_smooth", "g_m_smooth", "g_m_sparsity", "g_p_photo"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: replica synchronisation at construction, chunked / overlapped all-reduce, layout check, fixed module order
+def _spawn(target, world=2, timeout=180, extra=()):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, out) + tuple(extra)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout)
+        assert p.exitcode == 0
+    return dict(out.get(timeout=10) for _ in range(world))
+
+
+def _make_net(seed):
+    torch.manual_seed(seed)
+    return torch.nn.ModuleDict({
+        "enc": torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.BatchNorm2d(4), torch.nn.ReLU()),
+        "dec": torch.nn.Sequential(torch.nn.Conv2d(4, 2, 3, padding=1)),
+        "head": torch.nn.Sequential(torch.nn.Linear(2, 3)),
+    })
+
+
+def _broadcast_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dd_b200.parallel import broadcast_module_state
+
+    net = _make_net(100 + rank)                       # every rank starts from different weights, as with unseeded train.py
+    net["enc"][1].running_mean.fill_(float(rank + 1))
+    net["enc"][1].num_batches_tracked.fill_(7 * (rank + 1))
+    n = broadcast_module_state(net, src=0)
+    flat = torch.cat([t.detach().double().reshape(-1) for t in list(net.parameters()) + list(net.buffers())])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    ok = all(torch.equal(g, gathered[0]) for g in gathered) and n == flat.numel()
+    ok = ok and float(net["enc"][1].running_mean[0]) == 1.0 and int(net["enc"][1].num_batches_tracked) == 7
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_construction_broadcast_makes_replicas_identical():
+    assert _spawn(_broadcast_worker) == {0: True, 1: True}
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dd_b200.parallel import GradArena, broadcast_module_state
+
+    net = _make_net(100 + rank)
+    broadcast_module_state(net)
+    named = [(f"{m}.{k}", p) for m in ("enc", "dec", "head") for k, p in net[m].named_parameters()]
+    arena = GradArena([p for _, p in named], world_size=world, names=[n for n, _ in named],
+                      chunk_ids=[n.split(".")[0] for n, _ in named], overlap=True)
+    ok = len(arena.chunks) == 3 and arena.chunks[0][0] == 0 and arena.chunks[-1][1] == arena.numel
+    opt = torch.optim.SGD([p for _, p in named], lr=0.1)
+    for step in range(3):
+        x = torch.randn(2, 3, 6, 6, generator=torch.Generator().manual_seed(10 * step + rank))
+        # `head` receives no gradient at all: its chunk must still be reduced (zeros) and never block the others
+        import copy
+        twin = copy.deepcopy(net)                       # same weights, plain autograd: the local gradient before any exchange
+        g = torch.autograd.grad(twin["dec"](twin["enc"](x)).pow(2).mean(), list(twin["enc"].parameters()) + list(twin["dec"].parameters()))
+        local = torch.cat([t.reshape(-1) for t in g] + [torch.zeros(sum(p.numel() for p in net["head"].parameters()))])
+        loss = net["dec"](net["enc"](x)).pow(2).mean()
+        loss.backward()
+        issued_in_backward = len(arena._works)
+        arena.all_reduce()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        ok = ok and torch.allclose(arena.flat, torch.stack(gathered).mean(0), rtol=1e-6, atol=1e-9)
+        ok = ok and arena.last_collectives == 3 and arena.check_views()
+        # step 0 only records which parameters receive gradients; afterwards the chunks leave from the autograd hooks
+        ok = ok and (issued_in_backward == 0 if step == 0 else issued_in_backward == 3)
+        opt.step()
+        arena.zero()
+    flat = torch.cat([p.detach().reshape(-1) for _, p in named])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    ok = ok and torch.equal(gathered[0], gathered[1])          # replicas stay bit-identical
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_chunked_allreduce_from_autograd_hooks_gloo_world2():
+    assert _spawn(_overlap_worker) == {0: True, 1: True}
+
+
+def _layout_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dd_b200.parallel import GradArena
+
+    net = _make_net(0)
+    named = [(f"{m}.{k}", p) for m in (("enc", "dec") if rank == 0 else ("dec", "enc")) for k, p in net[m].named_parameters()]
+    try:
+        GradArena([p for _, p in named], world_size=world, names=[n for n, _ in named])
+        ok = False
+    except RuntimeError as e:
+        ok = "layout" in str(e)
+    out.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_arena_layout_mismatch_between_ranks_is_refused():
+    assert _spawn(_layout_worker) == {0: True, 1: True}
+
+
+def test_module_and_parameter_order_do_not_depend_on_the_hash_seed():
+    """list(set(...)) over module names made the arena / Adam-state order differ between processes."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r); import options, networks\n"
+            "from dd_b200.parallel import layout_digest\n"
+            "opt = options.DynamoOptions().parse(args=['--weights_init', 'scratch', '--height', '64', '--width', '96'])\n"
+            "m = networks.Model(opt)\n"
+            "named = m.named_parameters_by_names(['Depth', 'Pose', 'CmpFlow', 'MotMask'])\n"
+            "assert [id(p) for _, p in named] == [id(p) for p in m.parameters_by_names(['MotMask', 'CmpFlow', 'Pose', 'Depth'])]\n"
+            "print(','.join(m.module_names), layout_digest([(n, p.numel()) for n, p in named]))\n") % PKG_DIR
+    outs = set()
+    for seed in ("1", "2", "77"):
+        env = dict(os.environ, PYTHONHASHSEED=seed)
+        outs.add(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
+    assert len(outs) == 1, outs
+    assert outs.pop().startswith("depth_enc,depth_dec,pose_enc,pose_dec,motion_enc,motion_dec,motion_mask ")
+
+
+PKG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dynamo-depth_b200")

@@ -4,7 +4,7 @@ RANSAC ground prior of fine_tune.  Tolerance 1e-4 relative on every loss entry."
 import pytest
 import torch
 
-from oracle.compare import assert_close_robust
+from oracle.compare import assert_close_robust, check_rel
 from oracle.golden_io import LOSS_CASE_NAMES, LossCase
 
 pytestmark = pytest.mark.gpu
@@ -45,7 +45,7 @@ def test_trainer_losses_match_reference(name):
     for k, ref in case.losses.items():
         got = losses[k]
         got = float(got.detach()) if torch.is_tensor(got) else float(got)
-        assert got == pytest.approx(ref, rel=1e-4, abs=1e-7), (k, got, ref)
+        check_rel(got, ref, 1e-4, abs_tol=1e-7, what=k)
     for k, ref in case.grads.items():
         got = leaves[k].grad
         assert got is not None, k

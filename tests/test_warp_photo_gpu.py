@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import view_synthesis as vs
-from oracle.compare import assert_close_robust
+from oracle.compare import assert_close_robust, check_rel
 from oracle.golden_io import LOSS_CASE_NAMES, LossCase
 
 pytestmark = pytest.mark.gpu
@@ -66,13 +66,13 @@ def test_photo_loss_and_grads_vs_oracle(name, keep_warped):
     cfg, o_out, o_leaves, o_losses = oracle_photo(case)
     wc, leaves, terms, loss, sums = cuda_photo(case, cfg, keep_warped=keep_warped)
     torch.cuda.synchronize()
-    assert float(loss) == pytest.approx(float(o_losses["loss"]), rel=1e-4)
-    assert float(terms["p_photo"]) == pytest.approx(float(o_losses["loss_term/p_photo"]), rel=1e-4)
+    check_rel(float(loss), float(o_losses["loss"]), 1e-4, what="loss vs oracle")
+    check_rel(float(terms["p_photo"]), float(o_losses["loss_term/p_photo"]), 1e-4, what="p_photo vs oracle")
     # the golden from the reference holds the same photometric term
-    assert float(terms["p_photo"]) == pytest.approx(case.losses["loss_term/p_photo"], rel=1e-4)
+    check_rel(float(terms["p_photo"]), case.losses["loss_term/p_photo"], 1e-4, what="p_photo vs reference golden")
     if cfg.bool_MotMask:
-        assert float(terms["c_consistency"]) == pytest.approx(float(o_losses["loss_term/c_consistency"]), rel=1e-4)
-        assert float(terms["c_consistency"]) == pytest.approx(case.losses["loss_term/c_consistency"], rel=1e-4)
+        check_rel(float(terms["c_consistency"]), float(o_losses["loss_term/c_consistency"]), 1e-4, what="c_consistency vs oracle")
+        check_rel(float(terms["c_consistency"]), case.losses["loss_term/c_consistency"], 1e-4, what="c_consistency vs reference golden")
     for k, ref in o_leaves.items():
         if ref.grad is None:
             continue
