@@ -530,9 +530,7 @@ __device__ __forceinline__ void emit_output(const ConvArgs& a, int b, int co, in
 
 }  // namespace dd
 
-#include "conv_tc.cuh"   // tcgen05 implicit-GEMM core (uses ConvArgs, build_tile_map, emit_output from above)
-#include "conv_tc2.cuh"  // experimental shared-memory staged variant (DD_TC_CONV=2)
-#include "conv_tc3.cuh"  // experimental weight-stationary variant of it (DD_TC_CONV=3)
+#include "conv_tc4.cuh"  // tcgen05 implicit-GEMM core of the 3x3 layers (uses ConvArgs, build_tile_map, emit_output from above)
 
 namespace dd {
 
@@ -1328,12 +1326,8 @@ static bool use_winograd(int ks, int cin, int cout) {
 
 static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose,
                     cudaStream_t st) {
-  if (use_tc3_conv(ks, args.Cin, args.Cout))  // experimental (DD_TC_CONV=3): weight-stationary staged-patch core, 3x3 layers
-    return run_conv_tc3(args, wt_buf, w_oihw, Cout_f, Cin_f, transpose, device_sms(), st);
-  if (use_tc2_conv(ks, args.Cin, args.Cout))  // experimental (DD_TC_CONV=2): staged-patch tensor-core core, 3x3 layers
-    return run_conv_tc2(args, wt_buf, w_oihw, Cout_f, Cin_f, transpose, device_sms(), st);
-  if (use_tc_conv(ks, args.Cin, args.Cout))   // tensor cores (3xTF32): every layer with more than 16 output channels
-    return run_conv_tc(args, ks, wt_buf, w_oihw, Cout_f, Cin_f, transpose, device_sms(), st);
+  if (use_tc4_conv(ks, args.Cin, args.Cout))  // tensor cores (3xTF32, fp32 accuracy): every 3x3 layer with more than 16 output channels
+    return run_conv_tc4(args, wt_buf, w_oihw, Cout_f, Cin_f, transpose, device_sms(), st);
   if (use_winograd(ks, args.Cin, args.Cout)) {
     args.cout_pad = round_up(args.Cout, WN_CO);
     const size_t wn = (size_t)args.Cin * args.cout_pad;
@@ -1420,9 +1414,8 @@ static ConvWs conv_ws(const dd_conv_desc* d) {
   const int Cin = d->C0 + d->C1;
   // prepared weights: the largest of the Winograd layout [16][Cin][cout_pad] and the tensor-core layout [Cout][KK][cin_pad]
   size_t wt_f = (size_t)round_up(Cin, 32) * (KK == 9 ? 16 : KK) * round_up(d->Cout, 32) * sizeof(float);
-  static const bool tc2 = getenv("DD_TC_CONV") != nullptr && (getenv("DD_TC_CONV")[0] == '2' || getenv("DD_TC_CONV")[0] == '3');
-  if (tc2 && KK == 9) {   // experimental staged-patch core: hi / lo weight blocks of the forward and of the transposed problem
-    const size_t f = conv_tc2_weight_bytes(Cin, d->Cout), t = conv_tc2_weight_bytes(d->Cout, Cin);
+  if (KK == 9) {   // tensor-core core: pre-split hi / lo weight blocks of the forward and of the transposed (data-gradient) problem
+    const size_t f = conv_tc4_weight_bytes(Cin, d->Cout), t = conv_tc4_weight_bytes(d->Cout, Cin);
     wt_f = wt_f > f ? wt_f : f;
     wt_f = wt_f > t ? wt_f : t;
   }

@@ -25,7 +25,9 @@ def test_trainer_resume_continues_schedule(tmp_path):
     tr = Trainer(_opt(tmp_path, "full"))
     tr.train()
     models = os.path.join(str(tmp_path), "full", "models")
-    assert sorted(os.listdir(models)) == ["disp_init_00", "disp_init_01", "motion_init_00"]
+    folders = lambda d: sorted(f for f in os.listdir(d) if os.path.isdir(os.path.join(d, f)))
+    assert os.path.isfile(os.path.join(models, "opt.json"))          # written at construction, as the reference does (Trainer.py:85)
+    assert folders(models) == ["disp_init_00", "disp_init_01", "motion_init_00"]
     first = ckpt.load_state(os.path.join(models, "disp_init_00"))
     assert (first["phase_name"], first["epoch"], first["step"], first["g_step"]) == ("disp_init", 0, 2, 2)
     assert tr.g_step == 6 and tr.phase_name == "motion_init"
@@ -35,7 +37,7 @@ def test_trainer_resume_continues_schedule(tmp_path):
     tr2.train()
     # the run picked up the weights of the checkpoint and went on with disp_init epoch 1, then motion_init
     models2 = os.path.join(str(tmp_path), "resumed", "models")
-    assert sorted(os.listdir(models2)) == ["disp_init_01", "motion_init_00"]
+    assert folders(models2) == ["disp_init_01", "motion_init_00"]
     assert tr2.g_step == 6 and tr2.phase_name == "motion_init"
     mid = ckpt.load_state(os.path.join(models2, "disp_init_01"))
     assert (mid["phase_name"], mid["epoch"], mid["step"], mid["g_step"]) == ("disp_init", 1, 4, 4)
