@@ -88,9 +88,11 @@ CONVS = [  # name, C0, C1, Cout, H, W (output), ksize, pad, act, up
 ]
 
 
-def bench_conv(B, reps):
+def bench_conv(B, reps, only=None):
     dev = torch.device("cuda")
     for name, C0, C1, Cout, h, w, ks, pad, act, up in CONVS:
+        if only and only not in name:
+            continue
         h0, w0 = (h, w) if up == "none" else (h // 2, w // 2)
         x0 = torch.randn(B, C0, h0, w0, device=dev, requires_grad=True)
         x1 = torch.randn(B, C1, h, w, device=dev, requires_grad=True) if C1 else None
@@ -111,10 +113,11 @@ if __name__ == "__main__":
     ap.add_argument("--what", default="all")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--only", default=None, help="substring of the convolution layer name")
     a = ap.parse_args()
     if a.what in ("warp", "all"):
         bench_warp(a.batch, a.reps)
     if a.what in ("warp0", "warp1", "warp2"):
         bench_warp(a.batch, a.reps, only=int(a.what[-1]))
     if a.what in ("conv", "all"):
-        bench_conv(a.batch, a.reps)
+        bench_conv(a.batch, a.reps, a.only)

@@ -22,6 +22,14 @@
 //   K block    : 8 input channels: weights [hi, lo][tap][chunk][BN][4] arrive by ONE cp.async.bulk per K block (pre-split
 //                by conv_prep_tc4_weights_kernel) and are used by all T tiles: T x 9 taps x 3 splits = 27 T MMAs per
 //                36 KB (BN = 64) of weights
+//   accuracy   : every accumulate of the tensor core truncates the running fp32 sum, so the error of a long reduction grows with
+//                the NUMBER of MMAs chained into one accumulator (measured 1.5e-5 rel-L2 at K = 2304 with all three 3xTF32
+//                terms in one accumulator).  The two small terms (lo x hi, hi x lo; 2^-11 of the result) therefore go to a
+//                SEPARATE correction accumulator and only hi x hi to the main one: a third of the truncation events on
+//                the large sum; the epilogue adds the two.  TMEM: columns [0, 256) main, [256, 512) correction, T x BN each.
+//   hand-over  : per M tile (tfull[t] / tempty[t]): in the last K block the issuer commits after each tile's MMAs, so the
+//                epilogue of tile 0 runs under the MMAs of tiles 1..T-1 and the next work item re-enters a tile's columns as
+//                soon as that tile has been read out.
 //   warps      : 0-3 producers (thread = patch positions; 8 coalesced channel loads, hi/lo split, 4 x 16-byte stores),
 //                4-7 epilogue (tcgen05.ld, bias / activation / residual / split stores through emit_output),
 //                8 MMA issuer (one thread), 9 weight loader (one thread)
@@ -36,11 +44,14 @@ constexpr int C4_WSTAGES = 2;     // weight ring
 constexpr int C4_PROD_THREADS = 128;
 constexpr int C4_EPI_WARP0 = 4, C4_MMA_WARP = 8, C4_W_WARP = 9;
 constexpr int C4_THREADS = 320;
+constexpr int C4_MAX_COUT = 1024;  // bias staged in shared memory (n_tiles * BN floats)
 
 struct ConvTc4Args {
   ConvArgs a;
   const float* wsplit;   // [n_tile][kb][hi, lo][tap][chunk][BN][4]
   int kb_total, n_tiles;
+  int bn;                // output channels per N tile = N of the MMAs (multiple of 16, <= 128)
+  int wstage_bytes;      // 2 * 9 * 2 * bn * 16
   int PW, pw_shift;      // patch width (32 or 64 positions, incl. the two halo columns)
   int T;                 // M tiles per patch
   int rows_out;          // output rows per patch = T * 128 / PW
@@ -49,17 +60,23 @@ struct ConvTc4Args {
   int np;                // patch positions (rows_out + 2) * PW
   int chunk_bytes;       // (np + 2) * 16: one lead and one tail position that only halo outputs read
   int pstage_bytes;      // 4 * chunk_bytes rounded up to 128
+  int debug;             // development only (DD_TC4_DEBUG): 1 = producers skip loads / stores, 2 = no weight copies, 4 = epilogue skips its work
 };
 
 __host__ __device__ constexpr int c4_wstage_bytes(int bn) { return 2 * 9 * 2 * bn * 16; }
-__host__ __device__ constexpr int c4_tmax(int bn) { return bn <= 64 ? 4 : 2; }
-__host__ __device__ constexpr int c4_pstage_max_bytes(int bn) { return (4 * (c4_tmax(bn) * 128 + 2 * 64 + 2) * 16 + 127) / 128 * 128; }
-__host__ __device__ constexpr int c4_smem_bytes(int bn) {
-  return 1024 + C4_WSTAGES * c4_wstage_bytes(bn) + C4_PSTAGES * c4_pstage_max_bytes(bn) + 256;
+__host__ __device__ constexpr int c4_tmax(int bn) { return 256 / bn < 4 ? 256 / bn : 4; }   // T * bn <= 256 TMEM columns per accumulator set
+constexpr int C4_TMAX = 4;
+constexpr int C4_SMEM_MAX = tc::SMEM_BUDGET - (C4_MAX_COUT + 32) * 4 - 1024;   // dynamic shared memory next to the static bias array
+
+// N tile: the output channels are split evenly into ceil(Cout / 128) tiles, each rounded up to the MMA's N granularity of 16
+// (e.g. 64 -> 64, 67 -> 80, 112 -> 112, 240 -> 2 x 128, 512 -> 4 x 128)
+static int c4_bn(int cout) {
+  const int n_tiles = (cout + 127) / 128;
+  return ((cout + n_tiles - 1) / n_tiles + 15) / 16 * 16;
 }
 
 static size_t conv_tc4_weight_bytes(int cin, int cout) {
-  const int bn = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+  const int bn = c4_bn(cout);
   return (size_t)((cout + bn - 1) / bn) * ((cin + C4_KC - 1) / C4_KC) * c4_wstage_bytes(bn);
 }
 
@@ -99,16 +116,32 @@ __device__ __forceinline__ uint64_t c4_desc(uint32_t addr, uint32_t lbo_bytes) {
   return d;
 }
 
-template <int BN>
+// one lane of the (converged) warp; always the same one, so that tcgen05.commit tracks the MMAs this lane issued
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void st_global_f32(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+template <int IL>
 __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_constant__ ConvTc4Args g) {
   using namespace tc;
-  constexpr int TMAX = c4_tmax(BN);
-  constexpr int NSLOT = TMAX + 1;                      // patch positions per producer thread: np <= TMAX * 128 + 128
-  constexpr int WSTAGE_BYTES = c4_wstage_bytes(BN);
-  constexpr int W_HALF = WSTAGE_BYTES / 2;             // hi (or lo) block
-  constexpr int W_TAP = 2 * BN * 16;                   // one tap: two chunks of BN rows
-  constexpr int SET_COLS = 256;                        // TMEM columns of one accumulator set (TMAX * BN <= 256)
-  static_assert(TMAX * BN <= SET_COLS, "accumulator set");
+  constexpr int NSLOT = C4_TMAX + 1;                   // patch positions per producer thread: np <= T * 128 + 128
+  constexpr int CORR_COL0 = 256;                       // TMEM columns [0, 256): hi x hi sums, [256, 512): lo x hi + hi x lo sums
+  const int BN = g.bn;                                 // (T * BN <= 256)
+  const int WSTAGE_BYTES = g.wstage_bytes;
+  const int W_HALF = WSTAGE_BYTES / 2;                 // hi (or lo) block
+  const int W_TAP = 2 * BN * 16;                       // one tap: two chunks of BN rows
   const ConvArgs& a = g.a;
 
   extern __shared__ uint8_t smem_raw[];
@@ -117,19 +150,21 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
   uint8_t* smem = smem_raw + (smem_base - raw_addr);
   const uint32_t w_base = smem_base;
   const uint32_t p_base = smem_base + C4_WSTAGES * WSTAGE_BYTES;
-  const uint32_t bar_off = C4_WSTAGES * WSTAGE_BYTES + C4_PSTAGES * c4_pstage_max_bytes(BN);
+  const uint32_t bar_off = C4_WSTAGES * WSTAGE_BYTES + C4_PSTAGES * g.pstage_bytes;
   const uint32_t bar_base = smem_base + bar_off;
   const uint32_t wfull = bar_base, wempty = bar_base + 16, pfull = bar_base + 32, pempty = bar_base + 56;
-  const uint32_t tfull = bar_base + 80, tempty = bar_base + 96;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 128);
+  const uint32_t tfull = bar_base + 80, tempty = bar_base + 112;     // one pair per M tile (TMAX <= 4)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 160);
+  __shared__ __align__(16) float bias_s[C4_MAX_COUT + 32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C4_WSTAGES; ++s) mbar_init(wfull + 8 * s, 1), mbar_init(wempty + 8 * s, 1);
     for (int s = 0; s < C4_PSTAGES; ++s) mbar_init(pfull + 8 * s, C4_PROD_THREADS), mbar_init(pempty + 8 * s, 1);
-    for (int s = 0; s < 2; ++s) mbar_init(tfull + 8 * s, 1), mbar_init(tempty + 8 * s, 4 * 32);
+    for (int s = 0; s < 4; ++s) mbar_init(tfull + 8 * s, 1), mbar_init(tempty + 8 * s, 4 * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < g.n_tiles * BN + 32; i += C4_THREADS) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
   if (warp == C4_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -176,20 +211,20 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
       for (int kb = 0; kb < g.kb_total; ++kb, ++pit) {
         const uint32_t ps = pit % C4_PSTAGES, pph = (pit / C4_PSTAGES) & 1u;
         float v[NSLOT][C4_KC];
+        if (g.debug & 1) {
+          mbar_wait(pempty + 8 * ps, pph ^ 1u);
+          mbar_arrive(pfull + 8 * ps);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < C4_KC; ++j) {
-          const int ch = kb * C4_KC + j;   // CTA-uniform
-          const float* p0 = img0 + (size_t)ch * plane0;
-          const float* p1 = img1 + (ptrdiff_t)(ch - C0) * (ptrdiff_t)plane1;
+          const int ch = kb * C4_KC + j;   // CTA-uniform: which source tensor this channel comes from is a uniform select
+          const bool from0 = ch < C0, live = ch < Call;
+          const float* pl = from0 ? img0 + (size_t)ch * plane0 : img1 + (ptrdiff_t)(ch - C0) * (ptrdiff_t)plane1;
 #pragma unroll
           for (int s = 0; s < NSLOT; ++s) {
-            float x = 0.f;
-            if (ch < C0) {
-              if (o0[s] >= 0) x = __ldg(p0 + o0[s]);
-            } else if (ch < Call) {
-              if (o1[s] >= 0) x = __ldg(p1 + o1[s]);
-            }
-            v[s][j] = x;
+            const int o = from0 ? o0[s] : o1[s];
+            v[s][j] = (live && o >= 0) ? __ldg(pl + o) : 0.f;
           }
         }
         mbar_wait(pempty + 8 * ps, pph ^ 1u);
@@ -222,6 +257,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
           const uint32_t ws = wit % C4_WSTAGES, wph = (wit / C4_WSTAGES) & 1u;
           mbar_wait(wempty + 8 * ws, wph ^ 1u);
           const float* src = g.wsplit + ((size_t)nt * g.kb_total + kb) * (WSTAGE_BYTES / 4);
+          if (g.debug & 2) {
+            mbar_arrive(wfull + 8 * ws);
+            continue;
+          }
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wfull + 8 * ws), "r"(WSTAGE_BYTES) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(w_base + ws * WSTAGE_BYTES),
                        "l"(src), "r"(WSTAGE_BYTES), "r"(wfull + 8 * ws)
@@ -232,73 +271,156 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
     __syncwarp();
   } else if (warp == C4_MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // D fp32 (bits 4-5 = 1), A / B tf32 (bits 7-9, 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 (17-22), M >> 4 (24-28)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)g.chunk_bytes, a_lo_off = 2u * (uint32_t)g.chunk_bytes;
-      uint32_t it = 0, tcount = 0;
-      for (int work = blockIdx.x; work < g.total_work; work += gridDim.x, ++tcount) {
-        const uint32_t buf = tcount & 1u, tph = (tcount >> 1) & 1u;
-        mbar_wait(tempty + 8 * buf, tph ^ 1u);
+    // The whole warp runs this code convergently (barrier waits, warp-uniform descriptor arithmetic in uniform registers);
+    // only the tcgen05 instructions sit under elect.sync.  (Wrapping the loop in `if (lane == 0)` makes ptxas emit an
+    // ELECT / BRA.U.ANY serialisation loop plus R2UR moves around EVERY MMA: ~100 clocks of issue per 32-clock MMA.)
+    // D fp32 (bits 4-5 = 1), A / B tf32 (bits 7-9, 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 (17-22), M >> 4 (24-28)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // descriptor = {low word: (address >> 4) | (LBO >> 4) << 16, high word: SBO >> 4 | version 1 << 14 | layout 0 << 29}
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+    const uint32_t B_LBO16 = (uint32_t)BN << 16;   // (BN * 16 bytes) >> 4
+    const uint32_t a_lbo16 = ((uint32_t)g.chunk_bytes >> 4) << 16, a_lo_delta = (2u * (uint32_t)g.chunk_bytes) >> 4;
+    int tapoff[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) tapoff[tap] = (tap / 3 - 1) * g.PW + (tap % 3 - 1);   // in 16-byte units
+    uint32_t it = 0, tcount = 0;
+    for (int work = blockIdx.x; work < g.total_work; work += gridDim.x, ++tcount) {
+      const uint32_t iph = tcount & 1u;
+      for (int kb = 0; kb < g.kb_total; ++kb, ++it) {
+        const uint32_t ws = it % C4_WSTAGES, wph = (it / C4_WSTAGES) & 1u;
+        const uint32_t ps = it % C4_PSTAGES, pph = (it / C4_PSTAGES) & 1u;
+        mbar_wait(wfull + 8 * ws, wph);
+        mbar_wait(pfull + 8 * ps, pph);
         tc_fence_after();
-        for (int kb = 0; kb < g.kb_total; ++kb, ++it) {
-          const uint32_t ws = it % C4_WSTAGES, wph = (it / C4_WSTAGES) & 1u;
-          const uint32_t ps = it % C4_PSTAGES, pph = (it / C4_PSTAGES) & 1u;
-          mbar_wait(wfull + 8 * ws, wph);
-          mbar_wait(pfull + 8 * ps, pph);
-          tc_fence_after();
-          const uint32_t b_hi = w_base + ws * WSTAGE_BYTES, b_lo = b_hi + W_HALF;
-          // patch position p lives at byte (p + 1) * 16 of its chunk; the first output position of M tile t is PW + 128 t
-          const uint32_t a_hi0 = p_base + ps * g.pstage_bytes + (uint32_t)(1 + g.PW) * 16u;
-          for (int t = 0; t < g.T; ++t) {
-            const uint32_t d_tmem = tmem_base + buf * SET_COLS + (uint32_t)(t * BN);
+        const uint32_t b0 = (w_base + ws * WSTAGE_BYTES) >> 4;                                  // hi block, tap 0
+        // patch position p lives at byte (p + 1) * 16 of its chunk; the first output position of M tile t is PW + 128 t
+        const uint32_t a0 = ((p_base + ps * g.pstage_bytes) >> 4) + 1u + (uint32_t)g.PW;      // hi chunk 0, position PW
+        const bool last_kb = kb == g.kb_total - 1;
+        // M tiles are issued in groups of IL, round-robin inside a group, so that consecutive MMAs go to different
+        // accumulators: back-to-back MMAs into ONE accumulator (N = 64: 32 clocks of work each) expose the tensor pipe's
+        // read-modify-write latency (measured ~115 clocks per MMA with IL = 1).
+        for (int tg = 0; tg < g.T; tg += IL) {
+          if (kb == 0) {   // the previous work item's epilogue has read these tiles' columns
+#pragma unroll
+            for (int u = 0; u < IL; ++u)
+              if (tg + u < g.T) mbar_wait(tempty + 8 * (tg + u), iph ^ 1u);
+            tc_fence_after();
+          }
+          const uint32_t d0 = tmem_base + (uint32_t)(tg * BN);
+          const uint32_t at = a0 + (uint32_t)(tg * 128);
+          if (elect_one()) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-              const uint32_t a_hi = a_hi0 + (uint32_t)((t * 128 + dy * g.PW + dx) * 16);
-              const uint64_t da_hi = c4_desc(a_hi, a_lbo), da_lo = c4_desc(a_hi + a_lo_off, a_lbo);
-              const uint64_t db_hi = c4_desc(b_hi + tap * W_TAP, BN * 16), db_lo = c4_desc(b_lo + tap * W_TAP, BN * 16);
-              umma_tf32(d_tmem, da_lo, db_hi, idesc, (kb > 0 || tap > 0) ? 1u : 0u);
-              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-              umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+              const uint32_t ah = at + (uint32_t)tapoff[tap];
+              const uint64_t db_hi = desc64((b0 + tap * (W_TAP >> 4)) | B_LBO16, DESC_HI);
+              const uint64_t db_lo = desc64((b0 + (W_HALF >> 4) + tap * (W_TAP >> 4)) | B_LBO16, DESC_HI);
+              const uint32_t acc = (kb > 0 || tap > 0) ? 1u : 0u;
+#pragma unroll
+              for (int u = 0; u < IL; ++u)
+                if (tg + u < g.T)
+                  umma_tf32(d0 + u * BN + CORR_COL0, desc64((ah + u * 128 + a_lo_delta) | a_lbo16, DESC_HI), db_hi, idesc, acc);
+#pragma unroll
+              for (int u = 0; u < IL; ++u)
+                if (tg + u < g.T) umma_tf32(d0 + u * BN + CORR_COL0, desc64((ah + u * 128) | a_lbo16, DESC_HI), db_lo, idesc, 1u);
+#pragma unroll
+              for (int u = 0; u < IL; ++u)
+                if (tg + u < g.T) umma_tf32(d0 + u * BN, desc64((ah + u * 128) | a_lbo16, DESC_HI), db_hi, idesc, acc);
+            }
+            if (last_kb) {   // these tiles' accumulators are complete
+#pragma unroll
+              for (int u = 0; u < IL; ++u)
+                if (tg + u < g.T) tc_commit(tfull + 8 * (tg + u));
             }
           }
+          __syncwarp();
+        }
+        if (elect_one()) {
           tc_commit(pempty + 8 * ps);   // patch stage and weight stage may be refilled once these MMAs have read them
           tc_commit(wempty + 8 * ws);
         }
-        tc_commit(tfull + 8 * buf);     // all T accumulators of this work item complete
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: warp ew owns TMEM lanes 32 ew .. 32 ew + 31
     const int ew = warp - C4_EPI_WARP0;
+    const size_t HoWo = (size_t)a.Ho * a.Wo;
     uint32_t tcount = 0;
     for (int work = blockIdx.x; work < g.total_work; work += gridDim.x, ++tcount) {
       const int nt = work % g.n_tiles, patch = work / g.n_tiles;
       const int b = patch / tiles_img, rem = patch - b * tiles_img, ty = rem / g.tiles_x;
       const int y0 = ty * g.rows_out, x0 = (rem - ty * g.tiles_x) * cols_out;
-      const uint32_t buf = tcount & 1u, tph = (tcount >> 1) & 1u;
-      mbar_wait(tfull + 8 * buf, tph);
-      tc_fence_after();
+      const uint32_t iph = tcount & 1u;
 #pragma unroll 1
       for (int t = 0; t < g.T; ++t) {
+        mbar_wait(tfull + 8 * t, iph);
+        tc_fence_after();
         const int q = t * 128 + ew * 32 + lane;          // linear position relative to patch row 1, column 0
         const int r = q >> g.pw_shift, c = q & (g.PW - 1);
-        const bool keep = c >= 1 && c <= cols_out;
-        const int y = y0 + r, x = keep ? x0 + c - 1 : (1 << 28);   // emit_output drops x >= Wo
+        const int y = y0 + r, x = x0 + c - 1;
+        const bool valid = c >= 1 && c <= cols_out && y < a.Ho && x < a.Wo;
+        const size_t pix = (size_t)y * a.Wo + x;
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
+        for (int cb = 0; cb < ((g.debug & 4) ? 0 : (BN + 31) / 32); ++cb) {
           const int co0 = nt * BN + cb * 32;
           if (co0 >= a.Cout) break;   // warp-uniform
-          uint32_t rr[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + buf * SET_COLS + (uint32_t)(t * BN + cb * 32), rr);
+          // Loads first, stores last: the output pointers are generic, so the compiler must assume that a store may alias
+          // the shared-memory bias (or the residual) and would otherwise serialise load -> add -> store per channel.
+          float v[32];
+          {
+            uint32_t rm[32], rc[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t * BN + cb * 32);
+            tmem_ld32(taddr, rm);
+            tmem_ld32(taddr + CORR_COL0, rc);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) emit_output(a, b, co0 + j, y, x, __uint_as_float(rr[j]));
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + co0 + 4 * j4);
+              v[4 * j4 + 0] = (__uint_as_float(rm[4 * j4 + 0]) + __uint_as_float(rc[4 * j4 + 0])) + b4.x;
+              v[4 * j4 + 1] = (__uint_as_float(rm[4 * j4 + 1]) + __uint_as_float(rc[4 * j4 + 1])) + b4.y;
+              v[4 * j4 + 2] = (__uint_as_float(rm[4 * j4 + 2]) + __uint_as_float(rc[4 * j4 + 2])) + b4.z;
+              v[4 * j4 + 3] = (__uint_as_float(rm[4 * j4 + 3]) + __uint_as_float(rc[4 * j4 + 3])) + b4.w;
+            }
+          }
+          if (a.act != DD_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+          }
+          // destination of channel co: `out` (C_a channels) below the split, `out1` (Cout - split channels) from it on
+          const int C_a = a.split > 0 ? a.split : a.Cout;
+          const int n_here = min(32, min(a.Cout, (nt + 1) * BN) - co0);   // channels of this block that exist (and belong to this N tile)
+          const bool in0 = co0 + n_here <= C_a, in1 = a.split > 0 && co0 >= a.split;
+          if (in0 || in1) {
+            // fast path (the block lies in one destination tensor): one pointer, one predicated store per channel
+            float* p = in0 ? a.out + ((size_t)b * C_a + co0) * HoWo + pix
+                           : (a.out1 == nullptr ? nullptr : a.out1 + ((size_t)b * (a.Cout - a.split) + (co0 - a.split)) * HoWo + pix);
+            const bool st_ok = valid && p != nullptr;
+            if (a.residual != nullptr) {   // (only single-tensor forward layers carry a residual; same offsets as `out`)
+              const float* rp = a.residual + (p - a.out);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (st_ok && j < n_here) v[j] += __ldg(rp + (size_t)j * HoWo);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (st_ok && j < n_here) st_global_f32(p + (size_t)j * HoWo, v[j]);
+          } else {
+            // the split boundary falls inside this block of 32 channels (e.g. a 3-channel x0 in front of the skip tensor)
+            float* base0 = a.out + (size_t)b * C_a * HoWo + pix;
+            float* base1 = a.out1 == nullptr ? nullptr : a.out1 + (size_t)b * (a.Cout - a.split) * HoWo + pix;
+#pragma unroll 1
+            for (int j = 0; j < n_here; ++j) {
+              const int co = co0 + j;   // warp-uniform
+              float* d = co < C_a ? base0 + (size_t)co * HoWo : (base1 == nullptr ? nullptr : base1 + (size_t)(co - a.split) * HoWo);
+              float val = v[0];
+#pragma unroll
+              for (int q = 1; q < 32; ++q) val = j == q ? v[q] : val;    // register array: select, do not index
+              if (valid && d != nullptr) st_global_f32(d, val);
+            }
+          }
         }
+        tc_fence_before();
+        mbar_arrive(tempty + 8 * t);
       }
-      tc_fence_before();
-      mbar_arrive(tempty + 8 * buf);
     }
   }
 
@@ -310,17 +432,21 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
   }
 }
 
-template <int BN>
+static int c4_dynamic_smem(const ConvTc4Args& g) {
+  const int need = 1024 + C4_WSTAGES * g.wstage_bytes + C4_PSTAGES * g.pstage_bytes + 256;
+  return need < 120 * 1024 ? 120 * 1024 : need;   // more than half of the SM: one CTA per SM, which owns all 512 TMEM columns
+}
+
 static int launch_conv_tc4(const ConvTc4Args& g, int sms, cudaStream_t st) {
-  constexpr int SMEM = c4_smem_bytes(BN);
-  static_assert(SMEM <= tc::SMEM_BUDGET, "conv_tc4: shared memory budget");
+  constexpr int IL = 2;   // M tiles interleaved per issue group (1, 2 and 4 measured the same)
   static bool configured = false;
   if (!configured) {
-    DD_CHECK_CUDA(cudaFuncSetAttribute(conv_tc4_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BUDGET));
+    DD_CHECK_CUDA(cudaFuncSetAttribute(conv_tc4_kernel<IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C4_SMEM_MAX));
     configured = true;
   }
-  // more than half of the SM's shared memory in every configuration: one CTA per SM, which owns all 512 TMEM columns
-  conv_tc4_kernel<BN><<<g.total_work < sms ? g.total_work : sms, C4_THREADS, SMEM < 120 * 1024 ? 120 * 1024 : SMEM, st>>>(g);
+  const int smem = c4_dynamic_smem(g);
+  DD_REQUIRE(smem <= C4_SMEM_MAX, "conv_tc4_kernel: %d bytes of shared memory needed (bn %d, T %d)", smem, g.bn, g.T);
+  conv_tc4_kernel<IL><<<g.total_work < sms ? g.total_work : sms, C4_THREADS, smem, st>>>(g);
   dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
@@ -329,8 +455,12 @@ static int launch_conv_tc4(const ConvTc4Args& g, int sms, cudaStream_t st) {
 // Tensor cores are the default for every 3x3 layer the Winograd kernels used to take; DD_TC_CONV=0 restores those.
 static bool use_tc4_conv(int ks, int cin, int cout) {
   static const char* env = getenv("DD_TC_CONV");
-  static const bool off = env != nullptr && env[0] == '0';
-  return !off && ks == 3 && cout > 16 && cin >= 8;
+  static const bool off = env != nullptr && env[0] == '0', all = env != nullptr && env[0] == '2';
+  if (off || ks != 3 || cout <= 16 || cin < 8) return false;
+  // <= 32 output channels: an MMA with N = 32 still pays the full A-operand fetch (40 clocks for 16 clocks of math, see
+  // dev/micro/mma_rate.cu) and these layers have few K blocks per work item; the Winograd CUDA-core kernel is level or
+  // ahead there (32 -> 32 at 96x320: 0.51 ms vs 0.63 ms).  DD_TC_CONV=2 forces the tensor-core path for tests.
+  return all || cout > 32;
 }
 
 static int run_conv_tc4(const ConvArgs& args, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose, int sms,
@@ -339,9 +469,12 @@ static int run_conv_tc4(const ConvArgs& args, float* wt_buf, const float* w_oihw
   ConvTc4Args g;
   memset(&g, 0, sizeof(g));
   g.a = args;
-  const int BN = args.Cout <= 32 ? 32 : (args.Cout <= 64 ? 64 : 128);
+  const int BN = c4_bn(args.Cout);
+  g.bn = BN;
+  g.wstage_bytes = c4_wstage_bytes(BN);
   g.n_tiles = (args.Cout + BN - 1) / BN;
   g.kb_total = (args.Cin + C4_KC - 1) / C4_KC;
+  DD_REQUIRE(g.n_tiles * BN <= C4_MAX_COUT, "conv_tc4_kernel: more than %d output channels", C4_MAX_COUT);
   const size_t wn = (size_t)g.n_tiles * g.kb_total * 9 * 2 * BN * 4;
   conv_prep_tc4_weights_kernel<<<(int)((wn + 255) / 256 < 592 ? (wn + 255) / 256 : 592), 256, 0, st>>>(w_oihw, wt_buf, Cout_f, Cin_f, g.n_tiles,
                                                                                                      g.kb_total, BN, transpose ? 1 : 0);
@@ -351,14 +484,20 @@ static int run_conv_tc4(const ConvArgs& args, float* wt_buf, const float* w_oihw
   g.pw_shift = g.PW == 32 ? 5 : 6;
   const int rows_per_tile = 128 / g.PW, cols_out = g.PW - 2;
   g.tiles_x = (args.Wo + cols_out - 1) / cols_out;
-  // M tiles per patch: the one with the fewest (rounds over the SMs) x (work per item), ties to the larger (more weight reuse)
+  // M tiles per patch: fewest (rounds over the SMs) x (clocks per work item); an MMA costs max(N / 2, 32 + N / 4) clocks
+  // (A-operand fetch bound below N = 128, dev/micro/mma_rate.cu), a K block ~600 clocks of hand-over, a tile's epilogue
+  // ~700 clocks per 32 channels.  Ties go to the larger T (more weight reuse).
   const int tmax = c4_tmax(BN);
-  long best_cost = -1;
+  double best_cost = -1.0;
+  g.T = 1;
   for (int T = 1; T <= tmax; ++T) {
     const int rows = T * rows_per_tile;
+    const int np = (rows + 2) * g.PW;
+    if (1024 + C4_WSTAGES * g.wstage_bytes + C4_PSTAGES * ((4 * (np + 2) * 16 + 127) / 128 * 128) + 256 > C4_SMEM_MAX) continue;
     const long items = (long)g.n_tiles * args.B * g.tiles_x * ((args.Ho + rows - 1) / rows);
     const long rounds = (items + sms - 1) / sms;
-    const long cost = rounds * (27L * T * BN / 2 + 256);   // MMA clocks per K block + a fixed per-K-block overhead
+    const double mma = BN / 2 > 32 + BN / 4 ? BN / 2 : 32 + BN / 4;
+    const double cost = rounds * (g.kb_total * (27.0 * T * mma + 600.0) + T * ((BN + 31) / 32) * 700.0);
     if (best_cost < 0 || cost <= best_cost) best_cost = cost, g.T = T;
   }
   g.rows_out = g.T * rows_per_tile;
@@ -367,9 +506,9 @@ static int run_conv_tc4(const ConvArgs& args, float* wt_buf, const float* w_oihw
   g.np = (g.rows_out + 2) * g.PW;
   g.chunk_bytes = (g.np + 2) * 16;
   g.pstage_bytes = (4 * g.chunk_bytes + 127) / 128 * 128;
-  if (BN == 32) return launch_conv_tc4<32>(g, sms, st);
-  if (BN == 64) return launch_conv_tc4<64>(g, sms, st);
-  return launch_conv_tc4<128>(g, sms, st);
+  static const char* dbg = getenv("DD_TC4_DEBUG");
+  g.debug = dbg != nullptr ? atoi(dbg) : 0;
+  return launch_conv_tc4(g, sms, st);
 }
 
 }  // namespace dd
