@@ -60,6 +60,7 @@ class Trainer:
         if self.opt.load_ckpt != "":
             self.load_model()
         self.base_model.to(self.device)
+        self.base_model.prepare_memory_format()     # before any gradient arena exists (see ResnetEncoder.to_channels_last)
         self.model = self.base_model          # no DDP wrapper: gradients are reduced through the arena
         self.world_size = int(os.environ.get("WORLD_SIZE", 1)) if getattr(self.opt, "ddp", False) else 1
         if self.world_size > 1:
@@ -99,8 +100,10 @@ class Trainer:
         self.num_steps_per_epoch = max(1, int(getattr(self.opt, "epoch_size", 1)))
         self.bool_automask = False
         self.arena = None
+        self._arena_checked = False
         self.optim = None
-        self.overlap_allreduce = True        # all-reduce arena chunks from autograd hooks while backward is still running
+        # all-reduce arena chunks from autograd hooks while backward is still running (DD_OVERLAP=0: after backward)
+        self.overlap_allreduce = os.environ.get("DD_OVERLAP", "1") != "0"
         if self.is_main() and getattr(self.opt, "model_name", "--") != "--":
             self.save_opt()                  # as the reference (Trainer.py:85)
 
@@ -134,6 +137,7 @@ class Trainer:
         self.arena = GradArena(params, world_size=self.world_size, names=[n for n, _ in named],
                                chunk_ids=[n.split(".", 1)[0] for n, _ in named], overlap=self.overlap_allreduce)
         self.param_names = self.arena.names
+        self._arena_checked = False
         kw = {"fused": True} if optm is optim.Adam else {}
         optimizer = optm(params, self.opt.learning_rate * lr_factor, **kw)
         sched = optim.lr_scheduler.StepLR(optimizer, self.opt.scheduler_step_size, 0.5)
@@ -209,6 +213,11 @@ class Trainer:
         """process_batch + backward + gradient all-reduce + Adam (reference: Trainer.py:147-151)."""
         outputs, losses = self.process_batch(inputs)
         losses["loss"].backward()
+        if not self._arena_checked:       # once per phase: every .grad must still alias the arena, or the exchange is void
+            if not self.arena.check_views():
+                raise RuntimeError("a parameter's .grad no longer aliases the gradient arena (was a module converted with "
+                                   ".to(memory_format=...) / .to(dtype) after setup_phase?)")
+            self._arena_checked = True
         self.arena.all_reduce()
         self.optim["optimizer"].step()
         self.optim["optimizer"].zero_grad(set_to_none=False)

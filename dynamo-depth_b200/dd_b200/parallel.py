@@ -84,7 +84,10 @@ class GradArena:
         off, last = 0, object()
         for j, p in enumerate(self.params):
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            # same strides as the parameter (channels_last ResNet weights): the fused optimiser requires it, and a dense
+            # parameter of n elements maps one-to-one onto its n-element slice of the arena
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            p.grad = self.flat[off:off + n].as_strided(p.size(), p.stride()) if dense else self.flat[off:off + n].view_as(p)
             cid = chunk_ids[keep[j]]
             if not self.chunks or cid != last:
                 self.chunks.append([off, off + n, [j]])
@@ -170,4 +173,5 @@ class GradArena:
     def check_views(self):
         """True if every parameter's .grad still aliases the arena (autograd accumulates in place)."""
         base = self.flat.untyped_storage().data_ptr()
-        return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in self.params)
+        return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base and p.grad.stride() == p.stride()
+                   for p in self.params)

@@ -118,6 +118,14 @@ class Model(nn.Module):
                     outputs[(name, prev, s)] = v
                     outputs[(name, nxt, s)] = v
 
+    def prepare_memory_format(self):
+        """One-time layout conversions of the PyTorch encoders (NHWC ResNet trunks on CUDA); call after .to(device) and
+        before optimisers / gradient arenas are built."""
+        for name in self.module_names:
+            mod = getattr(self, name)
+            if isinstance(mod, ResnetEncoder) and next(mod.parameters()).is_cuda:
+                mod.to_channels_last()
+
     def modules_by_names(self, network_names):
         """Sub-module names of the given networks in the fixed MODULE_ORDER, each once (motion_enc is shared)."""
         wanted = set(m for n in network_names for m in self.network2modules[n])

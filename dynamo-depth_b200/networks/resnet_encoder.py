@@ -56,12 +56,17 @@ class ResnetEncoder(nn.Module):
     # NCHW<->NHWC conversions and with the faster NHWC batch-norm kernels (same arithmetic, ~7 % of the bs32 step).
     channels_last = True
 
+    def to_channels_last(self):
+        """Convert the trunk's weights once.  Must happen BEFORE a gradient arena / optimiser is built over the parameters:
+        Module.to(memory_format=...) re-creates `.grad` tensors too, which would silently detach them from the arena."""
+        if self.channels_last and not getattr(self, "_cl_ready", False):
+            self.encoder.to(memory_format=torch.channels_last)
+            self._cl_ready = True
+
     def forward(self, input_image):
         e = self.encoder
         if self.channels_last and input_image.is_cuda:
-            if not getattr(self, "_cl_ready", False):
-                e.to(memory_format=torch.channels_last)
-                self._cl_ready = True
+            self.to_channels_last()
             input_image = input_image.contiguous(memory_format=torch.channels_last)
         x = e.relu(e.bn1(e.conv1((input_image - 0.45) / 0.225)))
         self.features = [x]

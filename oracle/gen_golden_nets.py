@@ -135,14 +135,27 @@ def model_forward_golden(ns, depth_model, H, W, B, seed, name):
     print(f"wrote {path}: {len(rec)} arrays, {os.path.getsize(path)/1024:.0f} KiB")
 
 
-def step_golden(ns):
+POSE_BIAS = [0.02, -0.03, 0.01, 0.18, 0.09, 0.05]   # x 0.01 in the decoder: ~2e-4 rad, (1.8, 0.9, 0.5) mm -> a (3.3, 1.7) px shift at 0.2 m
+
+
+def step_golden(ns, automask=True):
     """BASELINE config 1: tiny_kitti 192x640 bs2 monodepthv2, reference Trainer, 1 step forward+loss
-    (+ backward and one Adam step), phase disp_init, train mode, injected automask noise."""
+    (+ backward and one Adam step), phase disp_init, train mode, injected automask noise.
+    automask=False records the WELL-CONDITIONED variant of the same step (step_config1_tiny_kitti_posed.npz): at random
+    initial weights the predicted pose is the identity to ~1e-6, so every sampling coordinate sits ON the integer pixel
+    lattice, where floor() -- and with it the bilinear coordinate gradient -- flips under last-ulp differences, and with
+    auto-masking on almost every pixel is also a near-tie between the identity and the warped loss.  The variant switches
+    auto-masking off and adds POSE_BIAS to the pose head's output bias (a few-pixel, non-integer shift), after which the
+    gradients of all parameters can be compared tightly."""
     data_path = os.path.join(_refshim.REFERENCE_ROOT, "assets", "tiny_kitti") + "/"
     argv = ["-d", "kitti", "--depth_model", "monodepthv2", "--weights_init", "scratch", "-b", "2", "--data_path", data_path]
     tr = _refshim.make_reference_trainer(ns, argv, phase="disp_init", step=0, steps_per_epoch=100)
     synth.fill_state(tr.base_model, 21)
+    if not automask:
+        with torch.no_grad():
+            tr.base_model.pose_dec.pose2.bias[:6] += torch.tensor(POSE_BIAS)
     tr.setup_phase("disp_init")   # optimiser over the freshly filled parameters
+    tr.bool_automask = automask
     tr.set_train()
     files = ["2011_09_26/2011_09_26_drive_0001_sync 1 l"] * 2
     ds = tr.get_dataset(files, is_train=False, load_depth=False, load_mask=False)
@@ -179,7 +192,9 @@ def step_golden(ns):
         for k, p in getattr(tr.base_model, mod).named_parameters():
             if not k.startswith("net."):
                 rec[f"pchk:{mod}.{k}"] = chk(p)
-    path = os.path.join(GOLDEN_DIR, "step_config1_tiny_kitti.npz")
+    if not automask:   # images / intrinsics live in the automask file
+        rec = {k: v for k, v in rec.items() if k.startswith(("loss:", "gchk:", "chk:"))}
+    path = os.path.join(GOLDEN_DIR, "step_config1_tiny_kitti.npz" if automask else "step_config1_tiny_kitti_posed.npz")
     np.savez_compressed(path, **rec)
     print(f"wrote {path}: {len(rec)} arrays, {os.path.getsize(path)/1024:.0f} KiB, loss={rec['loss:loss']:.6f}")
 
@@ -189,3 +204,4 @@ def gen_step(ns):
     model_forward_golden(ns, "monodepthv2", 64, 96, 2, 31, "model_fwd_md2_64x96")
     model_forward_golden(ns, "litemono", 64, 96, 2, 32, "model_fwd_lite_64x96")
     step_golden(ns)
+    step_golden(ns, automask=False)

@@ -266,3 +266,27 @@ def test_module_and_parameter_order_do_not_depend_on_the_hash_seed():
 
 
 PKG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dynamo-depth_b200")
+
+
+def test_arena_views_follow_channels_last_parameters_and_detect_detached_grads():
+    """R2 finding: ResNet trunks are converted to channels_last; Module.to(memory_format=...) re-creates .grad tensors, which
+    silently detached them from the arena (their gradients were then never all-reduced).  The arena now mirrors the
+    parameter's strides (the fused optimiser requires equal strides) and check_views() reports a detached gradient."""
+    from dd_b200.parallel import GradArena
+
+    conv = torch.nn.Conv2d(4, 6, 3).to(memory_format=torch.channels_last)
+    lin = torch.nn.Linear(5, 3)
+    params = list(conv.parameters()) + list(lin.parameters())
+    arena = GradArena(params, world_size=1)
+    assert conv.weight.grad.stride() == conv.weight.stride() != conv.weight.contiguous().stride()
+    assert arena.check_views()
+    x = torch.randn(2, 4, 8, 8).contiguous(memory_format=torch.channels_last)
+    (conv(x).mean() + lin(torch.randn(2, 5)).sum()).backward()
+    assert arena.check_views() and float(arena.flat.abs().sum()) > 0
+    ref = torch.autograd.grad(torch.nn.functional.conv2d(x, conv.weight, conv.bias).mean(), conv.weight)[0]
+    assert torch.allclose(conv.weight.grad, ref)
+    # a late layout conversion replaces .grad: must be detected
+    conv2 = torch.nn.Conv2d(4, 6, 3)
+    arena2 = GradArena(list(conv2.parameters()), world_size=1)
+    conv2.to(memory_format=torch.channels_last)
+    assert not arena2.check_views()
