@@ -2,7 +2,11 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <stdlib.h>
 #include <string.h>
+#include <tuple>
 
 #include "dd_common.cuh"
 
@@ -40,6 +44,56 @@ int validate_desc(const dd_warp_desc* d) {
     }
   }
   return DD_OK;
+}
+
+// Texture objects over source tensors, cached by (device, pointer, shape): a texture object is only a descriptor of an
+// address range (no device memory is allocated, nothing is copied), so an entry stays valid for as long as a tensor of that
+// shape lives at that address.  Returns 0 (kernels then gather with plain loads) when the tensor does not meet the pitch-linear
+// requirements or DD_NO_TEX is set.
+cudaTextureObject_t source_texture(const float* ptr, int B, int H, int W) {
+  static const bool off = getenv("DD_NO_TEX") != nullptr;
+  const long long rows = (long long)B * 3 * H;
+  if (off || ptr == nullptr || ((uintptr_t)ptr & 511u) != 0 || (W * 4) % 32 != 0 || rows > 65000 || W > 65000) return 0;
+  struct Key {
+    int dev;
+    const float* ptr;
+    int W;
+    long long rows;
+    bool operator<(const Key& o) const { return std::tie(dev, ptr, W, rows) < std::tie(o.dev, o.ptr, o.W, o.rows); }
+  };
+  static std::map<Key, cudaTextureObject_t> cache;
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lock(mu);
+  const Key key{dev, ptr, W, rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  if (cache.size() >= 256) {   // bounded: drop everything (descriptors only) and start over
+    for (auto& kv : cache) cudaDestroyTextureObject(kv.second);
+    cache.clear();
+  }
+  cudaResourceDesc res;
+  memset(&res, 0, sizeof(res));
+  res.resType = cudaResourceTypePitch2D;
+  res.res.pitch2D.devPtr = const_cast<float*>(ptr);
+  res.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+  res.res.pitch2D.width = (size_t)W;
+  res.res.pitch2D.height = (size_t)rows;
+  res.res.pitch2D.pitchInBytes = (size_t)W * sizeof(float);
+  cudaTextureDesc td;
+  memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  cudaTextureObject_t tex = 0;
+  if (cudaCreateTextureObject(&tex, &res, &td, nullptr) != cudaSuccess) {
+    cudaGetLastError();   // not an error of the call: fall back to plain loads
+    tex = 0;
+  }
+  cache[key] = tex;
+  return tex;
 }
 
 int warp_photo_fwd_impl(const dd_warp_desc*, const dd_warp_aux*, float*, void*, size_t, cudaStream_t);

@@ -102,11 +102,36 @@ __device__ __forceinline__ Foot footprint(float ix, float iy, int H, int W) {
   return ft;
 }
 
-__device__ __forceinline__ float sample_plane(const float* __restrict__ img, int W, const Foot& ft) {
-  const float nw = __ldg(img + ft.y0 * W + ft.x0), ne = __ldg(img + ft.y0 * W + ft.x1);
-  const float sw = __ldg(img + ft.y1 * W + ft.x0), se = __ldg(img + ft.y1 * W + ft.x1);
-  return nw * (ft.wx0 * ft.wy0) + ne * (ft.wx1 * ft.wy0) + sw * (ft.wx0 * ft.wy1) + se * (ft.wx1 * ft.wy1);
+// The four texels of a sampling footprint.  With a texture object over the source tensor (all B*3 planes stacked as one
+// pitch-linear 2-D image of B*3*H rows, point filtering, clamp addressing) ONE tex2Dgather instruction returns them
+// exactly (no hardware interpolation: the weights stay fp32 in the kernel), through the texture pipe instead of four
+// address computations + four LSU gathers.  The gather is addressed at the centre of the 2x2 block, (x0 + 1, row + y0 + 1),
+// so which texels are returned does not depend on any rounding of the coordinate.  A texel beyond the right / bottom border
+// of a plane is replaced by whatever the clamp / the next plane holds -- its bilinear weight is exactly 0 in that case
+// (footprint(): x0 = W - 1 only for ix = W - 1).  tex == 0: plain loads.
+struct Quad {
+  float nw, ne, sw, se;
+};
+__device__ __forceinline__ Quad gather4(cudaTextureObject_t tex, const float* __restrict__ img, int W, int row_base, const Foot& ft) {
+  Quad q;
+  if (tex != 0) {
+    const float4 t = tex2Dgather<float4>(tex, (float)ft.x0 + 1.f, (float)(row_base + ft.y0) + 1.f, 0);
+    q.sw = t.x, q.se = t.y, q.ne = t.z, q.nw = t.w;   // (i, j+1), (i+1, j+1), (i+1, j), (i, j)
+  } else {
+    q.nw = __ldg(img + ft.y0 * W + ft.x0), q.ne = __ldg(img + ft.y0 * W + ft.x1);
+    q.sw = __ldg(img + ft.y1 * W + ft.x0), q.se = __ldg(img + ft.y1 * W + ft.x1);
+  }
+  return q;
 }
+__device__ __forceinline__ float blend(const Quad& q, const Foot& ft) {
+  return q.nw * (ft.wx0 * ft.wy0) + q.ne * (ft.wx1 * ft.wy0) + q.sw * (ft.wx0 * ft.wy1) + q.se * (ft.wx1 * ft.wy1);
+}
+__device__ __forceinline__ float sample_plane(cudaTextureObject_t tex, const float* __restrict__ img, int W, int row_base, const Foot& ft) {
+  return blend(gather4(tex, img, W, row_base, ft), ft);
+}
+
+// host side (api.cu): cached texture object over a (B,3,H,W) fp32 tensor, 0 when the tensor does not qualify
+cudaTextureObject_t source_texture(const float* ptr, int B, int H, int W);
 
 // Low-resolution operands (disp_s, flow_s, mask_s at levels > 0) are staged per tile in shared memory with 4-byte
 // cp.async copies: ((tile >> s) + 2)^2 texels per plane cover every tap the tile's pixels interpolate from.

@@ -38,6 +38,7 @@ struct BwdArgs {
   const float* grad_sums;
   float* partial_T;   // [num_ctas][2][12]
   float min_disp, disp_range;
+  cudaTextureObject_t tex[DD_MAX_FRAMES];   // source frames as textures (0: gather with plain loads)
 };
 
 // smem (floats): Y[3] | X[2][3] (PLANE2 each) | LID[2][CPLANE] | COEF[10][CPLANE] | GT[9][GPLANE]
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
           const Foot ft = footprint(unnormalise(g.gx, W), unnormalise(g.gy, H), H, W);
           const float* src = d.source[f] + (size_t)b * 3 * P;
   #pragma unroll
-          for (int ch = 0; ch < 3; ++ch) smem[SM_X + (f * 3 + ch) * PLANE2 + so] = sample_plane(src + ch * P, W, ft);
+          for (int ch = 0; ch < 3; ++ch) smem[SM_X + (f * 3 + ch) * PLANE2 + so] = sample_plane(a.tex[f], src + ch * P, W, (b * 3 + ch) * H, ft);
         }
       }
       __syncthreads();
@@ -476,11 +477,9 @@ __global__ void __launch_bounds__(WP_THREADS, 2) warp_photo_bwd_kernel(const __g
           float gix = 0.f, giy = 0.f;
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            const float* img = src + ch * P;
-            const float nw = __ldg(img + ft.y0 * W + ft.x0), ne = __ldg(img + ft.y0 * W + ft.x1);
-            const float sw = __ldg(img + ft.y1 * W + ft.x0), se = __ldg(img + ft.y1 * W + ft.x1);
-            gix += gcol[f][ch] * ((ne - nw) * ft.wy0 + (se - sw) * ft.wy1);
-            giy += gcol[f][ch] * ((sw - nw) * ft.wx0 + (se - ne) * ft.wx1);
+            const Quad q = gather4(a.tex[f], src + ch * P, W, (b * 3 + ch) * H, ft);
+            gix += gcol[f][ch] * ((q.ne - q.nw) * ft.wy0 + (q.se - q.sw) * ft.wy1);
+            giy += gcol[f][ch] * ((q.sw - q.nw) * ft.wx0 + (q.se - q.ne) * ft.wx1);
           }
           const float gpx = ft.live_x ? gix : 0.f, gpy = ft.live_y ? giy : 0.f;   // GridSampler.cuh:64-80
           const float iz = g.pr.iz;
@@ -701,6 +700,7 @@ int warp_photo_bwd_impl(const dd_warp_desc* desc, const float* grad_sums, const 
   args.partial_T = reinterpret_cast<float*>(workspace);
   args.min_disp = 1.f / desc->max_depth;
   args.disp_range = 1.f / desc->min_depth - 1.f / desc->max_depth;
+  for (int f = 0; f < DD_MAX_FRAMES; ++f) args.tex[f] = f < desc->num_frames ? source_texture(desc->source[f], desc->B, desc->H, desc->W) : 0;
   for (int s = 0; s < desc->num_scales; ++s) {
     const size_t p_lo = (size_t)(desc->H >> desc->scale[s]) * (desc->W >> desc->scale[s]);
     for (int f = 0; f < desc->num_frames; ++f) {

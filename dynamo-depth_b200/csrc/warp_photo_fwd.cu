@@ -26,6 +26,7 @@ struct FwdArgs {
   float* partial;   // [num_scales*DD_NSUM][num_ctas]
   float min_disp, disp_range;
   int has_aux;
+  cudaTextureObject_t tex[DD_MAX_FRAMES];   // source frames as textures (0: gather with plain loads)
 };
 
 // shared memory carve-up (floats): Y[3][34][35] | XI[3][34][35][2] | lo[2][5][16][16] (flow modes: low-resolution
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
         float col[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
-          col[ch] = sample_plane(src + ch * P, W, ft);                  // Trainer.py:281
+          col[ch] = sample_plane(a.tex[f], src + ch * P, W, (b * 3 + ch) * H, ft);   // Trainer.py:281
           X[(ch * PLANE1 + hr * PITCH1 + hc) * 2] = col[ch];
         }
         if (interior) {
@@ -430,6 +431,7 @@ int warp_photo_fwd_impl(const dd_warp_desc* desc, const dd_warp_aux* aux, float*
   args.partial = reinterpret_cast<float*>(workspace);
   args.min_disp = 1.f / desc->max_depth;
   args.disp_range = 1.f / desc->min_depth - 1.f / desc->max_depth;
+  for (int f = 0; f < DD_MAX_FRAMES; ++f) args.tex[f] = f < desc->num_frames ? source_texture(desc->source[f], desc->B, desc->H, desc->W) : 0;
   const dim3 grid(desc->W / TILE, desc->H / TILE, desc->B);
   const int num_ctas = grid.x * grid.y * grid.z;
   const int mode = (desc->flags & DD_FLAG_CMPFLOW) ? ((desc->flags & DD_FLAG_MOTMASK) ? 2 : 1) : 0;

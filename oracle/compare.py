@@ -52,3 +52,29 @@ def check_rel(got, ref, rel=1e-4, abs_tol=0.0, what=""):
     parity_log.record(CURRENT_CASE, what, max_abs_rel=err / (scale + 1e-30), limit=rel)
     assert err <= rel * scale + abs_tol, (what, err, scale, rel)
     return err / (scale + 1e-30)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Per-case gradient bounds of the golden loss cases (tests/golden/loss_*.npz), derived from the errors MEASURED on the
+# B200 (profiles/r02_parity_errors.json): wherever no discrete event is involved the CUDA path agrees with the reference to
+# ~1e-5 (rel-L2 <= 1.4e-5, max-abs <= 3.2e-5 of the tensor's scale on every tensor), so the bound is north_star's 1e-4.
+# Three cases contain discrete flips that an independent fp32 implementation cannot reproduce bit for bit:
+#   loss_maskinit_lite_32x64        per-pixel min over the two source frames flips on a few of the 2048 pixels (measured
+#                                    rel-L2 up to 1.6e-2, outliers up to 1.6e-2 on the 8x16 level-2 maps; pose 1.4e-3)
+#   loss_finetune_ground_lite_64x96 one floor() flip of a sampling coordinate (measured rel-L2 2.6e-3 on one map, 5e-5 outliers)
+#   loss_dispinit_lite_96x128       automask argmin near-ties; maps stay at 1.3e-5, the pose gradient moves by 1.4e-4
+# Their bounds are 3x the measured values.
+GRAD_BOUNDS_DEFAULT = dict(rtol=1e-4, max_outlier_frac=0.0, max_rel_l2=1e-4)
+GRAD_BOUNDS_FLIPS = {
+    "loss_maskinit_lite_32x64": {"map": dict(rtol=1e-4, max_outlier_frac=5e-2, max_rel_l2=5e-2),
+                                 "pose": dict(rtol=5e-3, max_outlier_frac=0.0, max_rel_l2=5e-3)},
+    "loss_finetune_ground_lite_64x96": {"map": dict(rtol=1e-4, max_outlier_frac=2e-4, max_rel_l2=8e-3),
+                                        "pose": dict(rtol=4e-4, max_outlier_frac=0.0, max_rel_l2=2e-4)},
+    "loss_dispinit_lite_96x128": {"map": dict(rtol=1e-4, max_outlier_frac=0.0, max_rel_l2=1e-4),
+                                  "pose": dict(rtol=6e-4, max_outlier_frac=0.0, max_rel_l2=5e-4)},
+}
+
+
+def grad_bounds(case_name, key):
+    kind = "pose" if (isinstance(key, tuple) and key[0] == "cam_T_cam") else "map"
+    return dict(GRAD_BOUNDS_FLIPS.get(case_name, {}).get(kind, GRAD_BOUNDS_DEFAULT))

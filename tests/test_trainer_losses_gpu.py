@@ -4,7 +4,7 @@ RANSAC ground prior of fine_tune.  Tolerance 1e-4 relative on every loss entry."
 import pytest
 import torch
 
-from oracle.compare import assert_close_robust, check_rel
+from oracle.compare import assert_close_robust, check_rel, grad_bounds
 from oracle.golden_io import LOSS_CASE_NAMES, LossCase
 
 pytestmark = pytest.mark.gpu
@@ -49,10 +49,7 @@ def test_trainer_losses_match_reference(name):
     for k, ref in case.grads.items():
         got = leaves[k].grad
         assert got is not None, k
-        if k[0] == "cam_T_cam":
-            assert_close_robust(got.cpu(), ref, rtol=2e-3, max_outlier_frac=0.0, max_rel_l2=2e-3, what=k)
-        else:
-            assert_close_robust(got.cpu(), ref, rtol=2e-4, what=k)
+        assert_close_robust(got.cpu(), ref, what=k, **grad_bounds(name, k))
 
 
 def test_materialised_outputs_through_trainer():
