@@ -161,10 +161,6 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
   }
   __syncthreads();
 
-  if (MODE >= 1) {
-    float* lo = smem_lo(smem);
-    for (int i = tid; i < 2 * 5 * LO_PLANE; i += WP_THREADS) lo[i] = 0.f;
-  }
   // issues the cp.async copies of level si's low-resolution patch (no-op for full-resolution levels)
   auto stage_patch = [&](int si) {
     const int shift = d.scale[si];
@@ -212,9 +208,23 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
 
     float s_cc[2] = {0.f, 0.f}, s_mag[2] = {0.f, 0.f};
     // ---- stage A: warp every halo pixel of both frames ---------------------------------------
-    for (int i = tid; i < HALO1 * HALO1; i += WP_THREADS) {
-      const int hr = i / HALO1, hc = i - hr * HALO1;
-      const bool interior = (hr >= 1) && (hr <= TILE) && (hc >= 1) && (hc <= TILE);
+    // Interior pixels: thread (warp w, lane l) owns column l, rows 4w .. 4w+3 (the mapping of stage B): the 2x2 centre taps of a
+    // 2^s block that bilinear down-sampling averages are then either in this thread (rows) or one shuffle away (columns), so the
+    // low-resolution by-products are reduced in registers -- no shared-memory atomics (CAS loops on this architecture).
+    // Pass 4 covers the 132 pixels of the halo ring with the first 132 threads.
+#pragma unroll 1
+    for (int pass = 0; pass < 5; ++pass) {
+      int hr, hc;
+      if (pass < 4) {
+        hr = 1 + 4 * warp + pass, hc = 1 + lane;
+      } else {
+        if (tid >= 2 * HALO1 + 2 * TILE) break;
+        if (tid < HALO1) hr = 0, hc = tid;
+        else if (tid < 2 * HALO1) hr = HALO1 - 1, hc = tid - HALO1;
+        else if (tid < 2 * HALO1 + TILE) hr = 1 + (tid - 2 * HALO1), hc = 0;
+        else hr = 1 + (tid - 2 * HALO1 - TILE), hc = HALO1 - 1;
+      }
+      const bool interior = pass < 4;
       const int r = reflect1(r0 - 1 + hr, H), c = reflect1(c0 - 1 + hc, W);
       const Taps ty = up_taps(r, shift, h), tx = up_taps(c, shift, w);
       // patch-relative tap indices (levels > 0)
@@ -276,12 +286,24 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
               }
             } else {             // levels > 0: bilinear down-sampling = mean of the 2x2 centre taps of each 2^s block
               const int half = 1 << (shift - 1), msk = (1 << shift) - 1;
-              const int rr = r & msk, cr = c & msk;
-              if ((rr == half - 1 || rr == half) && (cr == half - 1 || cr == half)) {
+              const int rr = pass & msk & 3, cr = lane & msk;   // row / column inside the block (rows: 4w + pass, r0 % 32 == 0)
+              const bool row_tap = shift == 3 ? ((4 * warp + pass) & 7) == 3 || ((4 * warp + pass) & 7) == 4 : (rr == half - 1 || rr == half);
+              const bool col_tap = cr == half - 1 || cr == half;
+              if (row_tap) {   // warp-uniform
+                // centre columns pair up as lanes (half-1, half) of the block: xor 1 (2x2), 3 (4x4), 7 (8x8); the writer lane adds
+                // the block's second centre row onto the first with a plain read-modify-write (same thread owns both rows; at
+                // level 3 the two rows belong to neighbouring warps and go to two partial planes that stage C adds)
+                const bool first_row = shift == 1 ? (pass & 1) == 0 : (shift == 2 ? pass == 1 : true);
                 const int tl = TILE >> shift;
-                float* lo = smem_lo(smem) + f * 5 * LO_PLANE + ((hr - 1) >> shift) * tl + ((hc - 1) >> shift);
-                atomicAdd(lo, 0.25f * g.res.x), atomicAdd(lo + LO_PLANE, 0.25f * g.res.y), atomicAdd(lo + 2 * LO_PLANE, 0.25f * g.res.z);
-                atomicAdd(lo + 3 * LO_PLANE, 0.25f * g.dsx), atomicAdd(lo + 4 * LO_PLANE, 0.25f * g.dsy);
+                float* lo = smem_lo(smem) + f * 5 * LO_PLANE + ((4 * warp + pass) >> shift) * tl + (lane >> shift) +
+                            (shift == 3 && (warp & 1) ? LO_PLANE / 2 : 0);
+                const float v[5] = {g.res.x, g.res.y, g.res.z, g.dsx, g.dsy};
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                  const float mine = col_tap ? v[q] : 0.f;
+                  const float pair = 0.25f * (mine + __shfl_xor_sync(0xffffffffu, mine, msk));
+                  if (cr == half - 1) lo[q * LO_PLANE] = first_row ? pair : lo[q * LO_PLANE] + pair;
+                }
               }
             }
           }
@@ -347,10 +369,8 @@ __global__ void __launch_bounds__(WP_THREADS, (MODE == 0 ? 4 : 3)) warp_photo_fw
           float* lo = smem_lo(smem) + f * 5 * LO_PLANE + i;
           float acc[5];
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            acc[k] = lo[k * LO_PLANE];
-            lo[k * LO_PLANE] = 0.f;          // ready for the next level
-          }
+          for (int k = 0; k < 5; ++k)   // (level 3: the two centre rows of a block come from two warps)
+            acc[k] = lo[k * LO_PLANE] + (shift == 3 ? lo[k * LO_PLANE + LO_PLANE / 2] : 0.f);
           const float mag = acc[3] * acc[3] + acc[4] * acc[4];          // Trainer.py:396
           s_mag[f] += mag;
           if (a.has_aux && a.aux.mag[si][f]) a.aux.mag[si][f][(size_t)b * p_lo + ol] = mag;

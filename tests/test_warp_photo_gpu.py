@@ -79,10 +79,12 @@ def test_photo_loss_and_grads_vs_oracle(name, keep_warped):
         got = leaves[k].grad
         assert got is not None, k
         bounds = grad_bounds(name, k)
-        if name == "loss_dispinit_lite_96x128" and k[0] != "cam_T_cam":
+        if name == "loss_dispinit_lite_96x128":
             # here the comparison partner is the ORACLE, whose own automask argmin flips against the reference on this case
-            # (oracle vs reference golden: 8e-3 rel-L2; CUDA path vs the same golden: 1.3e-5, tests/test_trainer_losses_gpu.py)
-            bounds = dict(rtol=1e-4, max_outlier_frac=1.2e-3, max_rel_l2=2.5e-2)
+            # (oracle vs reference golden: 8e-3 rel-L2 on the level-0 map, 8e-4 on the pose gradient; CUDA path vs the same
+            # golden: 1.3e-5 / 1.4e-4, tests/test_trainer_losses_gpu.py)
+            bounds = dict(rtol=3e-3, max_outlier_frac=0.0, max_rel_l2=2.5e-3) if k[0] == "cam_T_cam" else \
+                dict(rtol=1e-4, max_outlier_frac=1.2e-3, max_rel_l2=2.5e-2)
         assert_close_robust(got.cpu(), ref.grad, what=k, **bounds)
 
 
