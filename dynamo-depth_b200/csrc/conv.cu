@@ -1253,6 +1253,12 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __rest
   }
 }
 
+}  // namespace dd
+
+#include "conv_wgrad_tc.cuh"  // tcgen05 weight gradient of the 3x3 layers (uses VirtIn, conv_tc4.cuh helpers)
+
+namespace dd {
+
 // ---- host side ---------------------------------------------------------------------------------
 
 static int device_sms() {
@@ -1386,7 +1392,7 @@ static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, 
 }
 
 struct ConvWs {
-  size_t wt, up, gconv, wtd, gpad, total;
+  size_t wt, up, gconv, wtd, gpad, slabs, total;
   size_t fwd_bytes;   // what the forward pass needs (prepared weights + materialised up-sampling)
 };
 
@@ -1428,7 +1434,8 @@ static ConvWs conv_ws(const dd_conv_desc* d) {
   w.fwd_bytes = w.gconv;
   w.wtd = w.gconv + align256((size_t)d->B * d->Cout * d->H * d->W * sizeof(float));
   w.gpad = w.wtd + align256(wt_d);
-  w.total = w.gpad + align256((size_t)d->B * Cin * Hp * Wp * sizeof(float));
+  w.slabs = w.gpad + align256((size_t)d->B * Cin * Hp * Wp * sizeof(float));
+  w.total = w.slabs + (use_tc_wgrad(d->ksize, Cin, d->Cout) ? align256(conv_wgrad_tc_slab_bytes(d->B, d->H, d->W, Cin, d->Cout, device_sms())) : 0);
   return w;
 }
 
@@ -1470,7 +1477,8 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     g = gc;
   }
   static const bool no_wino_wgrad = getenv("DD_NO_WINO_WGRAD") != nullptr;
-  const bool wino_wgrad = grad_weight && !no_wino_wgrad && use_winograd(d->ksize, Cin, d->Cout);
+  const bool tc_wgrad = grad_weight && use_tc_wgrad(d->ksize, Cin, d->Cout);
+  const bool wino_wgrad = grad_weight && !tc_wgrad && !no_wino_wgrad && use_winograd(d->ksize, Cin, d->Cout);
   if (grad_bias) DD_CHECK_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d->Cout * sizeof(float), st));
   if (grad_bias && !wino_wgrad) {   // (the Winograd weight-gradient kernel sums the bias gradient on the way)
     const size_t total = (size_t)d->B * d->H * d->W;
@@ -1480,7 +1488,15 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     conv_bias_grad_kernel<<<dim3(d->Cout, chunks), 256, 0, st>>>(g, grad_bias, d->B, d->Cout, d->H * d->W);
     dd::count_launches(1);
   }
-  if (grad_weight) {
+  if (tc_wgrad) {   // tensor cores: partial sums per work item in workspace slabs, deterministic reduction (no memset, no atomics)
+    WgradTcArgs wt;
+    memset(&wt, 0, sizeof(wt));
+    wt.vin = materialise_up(d, workspace, ws, st);
+    wt.g = g, wt.B = d->B, wt.H = d->H, wt.W = d->W, wt.Cin = Cin, wt.Cout = d->Cout;
+    wt.slabs = reinterpret_cast<float*>((char*)workspace + ws.slabs);
+    rc = run_conv_wgrad_tc(wt, grad_weight, device_sms(), st);
+    if (rc != DD_OK) return rc;
+  } else if (grad_weight) {
     DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));
     if (wino_wgrad) {
       WinoWgradArgs ww;

@@ -51,7 +51,9 @@ def test_conv_fwd_bwd(case):
     from dd_b200.functional import conv2d_fused
 
     B, C0, C1, Cout, H, W, ks, pad, act, up, use_res = case
-    g = torch.Generator(device="cuda").manual_seed(hash(case) % 10000)
+    # fixed seed per case (hash() of a tuple holding strings changes with PYTHONHASHSEED: a ReLU / ELU input within ~1e-6 of
+    # zero then flips the activation derivative in one run out of ~50 and fails the data-gradient comparison spuriously)
+    g = torch.Generator(device="cuda").manual_seed(1000 + CASES.index(case))
     h0, w0 = (H, W) if up == "none" else (H // 2, W // 2)
     x0 = torch.randn(B, C0, h0, w0, device="cuda", generator=g, requires_grad=True)
     x1 = torch.randn(B, C1, H, W, device="cuda", generator=g, requires_grad=True) if C1 else None
