@@ -318,8 +318,11 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ slabs, float* _
 
 static bool use_tc_wgrad(int ks, int cin, int cout) {
   static const char* env = getenv("DD_TC_WGRAD");
-  static const bool off = env != nullptr && env[0] == '0';
-  return !off && ks == 3 && cout > 16 && cin >= 8;
+  static const bool off = env != nullptr && env[0] == '0', all = env != nullptr && env[0] == '2';
+  if (off || ks != 3 || cout <= 16 || cin < 8) return false;
+  // <= 32 output channels: N = 32 MMAs are bound by the A-operand fetch (dev/micro/mma_rate.cu); the Winograd weight gradient is
+  // level or ahead there (32 -> 32 at 96x320: 1.46 vs 1.52 ms backward).  DD_TC_WGRAD=2 forces the tensor-core path for tests.
+  return all || cout > 32;
 }
 
 static int wgrad_tc_bn(int cout) {
