@@ -1480,7 +1480,7 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
   const bool tc_wgrad = grad_weight && use_tc_wgrad(d->ksize, Cin, d->Cout);
   const bool wino_wgrad = grad_weight && !tc_wgrad && !no_wino_wgrad && use_winograd(d->ksize, Cin, d->Cout);
   if (grad_bias) DD_CHECK_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)d->Cout * sizeof(float), st));
-  if (grad_bias && !wino_wgrad) {   // (the Winograd weight-gradient kernel sums the bias gradient on the way)
+  if (grad_bias && !wino_wgrad && !tc_wgrad) {   // (the Winograd / tensor-core weight-gradient kernels sum the bias gradient on the way)
     const size_t total = (size_t)d->B * d->H * d->W;
     int chunks = (int)((total + 256 * 8 - 1) / (256 * 8));              // >= 8 elements per thread
     const int cap = (148 * 8 + d->Cout - 1) / d->Cout;                   // ~8 CTAs per SM over all channels
@@ -1494,6 +1494,7 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     wt.vin = materialise_up(d, workspace, ws, st);
     wt.g = g, wt.B = d->B, wt.H = d->H, wt.W = d->W, wt.Cin = Cin, wt.Cout = d->Cout;
     wt.slabs = reinterpret_cast<float*>((char*)workspace + ws.slabs);
+    wt.gb = grad_bias;
     rc = run_conv_wgrad_tc(wt, grad_weight, device_sms(), st);
     if (rc != DD_OK) return rc;
   } else if (grad_weight) {

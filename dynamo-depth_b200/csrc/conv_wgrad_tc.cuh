@@ -54,6 +54,7 @@ struct WgradTcArgs {
   int rows_total;        // B * strips * H  (strip rows, image-major, then strip, then y)
   int rows_per_split, splits;
   float* slabs;          // [ci_tile][co_tile][split][dy 3][bn][128]
+  float* gb;             // optional (Cout,) bias gradient, zero-initialised: summed by the work items of input-channel tile 0
 };
 
 __host__ __device__ constexpr int wt_gslot_bytes(int bn) { return 2 * WT_CHUNKS * bn * 16; }
@@ -172,6 +173,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     const int gw = warp - WT_G_WARP0;
     const size_t gplane = (size_t)a.H * a.W;
     const bool vec = (a.W & 3) == 0;
+    const bool do_bias = a.gb != nullptr && cit == 0;   // every gradient pixel passes through exactly one work item of tile 0
+    float bsum[20];
+#pragma unroll
+    for (int q = 0; q < 20; ++q) bsum[q] = 0.f;
     for (int sr = row_a + gw; sr < row_b; sr += 4) {
       const uint32_t git = (uint32_t)(sr - row_a);
       const int b = sr / strip_rows, rem = sr - b * strip_rows, strip = rem / a.H, y = rem - strip * a.H;
@@ -204,10 +209,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         for (int q = 0; q < 10; ++q) {
           const int idx = lane + 32 * (q + 10 * half), co = idx >> 3, ck = idx & 7;
           if (co < BN) split_store(hi_base + ck * (BN * 16) + co * 16, lo_base + ck * (BN * 16) + co * 16, gv[q]);
+          if (half == 0) bsum[q] += (gv[q].x + gv[q].y) + (gv[q].z + gv[q].w);
+          else bsum[q + 10] += (gv[q].x + gv[q].y) + (gv[q].z + gv[q].w);
         }
       }
       fence_async_smem();
       mbar_arrive(gfull + 8 * slot);
+    }
+    if (do_bias) {   // lanes 8k .. 8k+7 hold the eight 4-pixel pieces of channel (lane >> 3) + 4 q: reduce, one atomic per channel
+#pragma unroll
+      for (int q = 0; q < 20; ++q) {
+        float v = bsum[q];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        const int co = (lane >> 3) + 4 * q;
+        if ((lane & 7) == 0 && co < BN && co0 + co < a.Cout) atomicAdd(a.gb + co0 + co, v);
+      }
     }
   } else if (warp == WT_MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
