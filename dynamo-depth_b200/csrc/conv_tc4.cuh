@@ -116,16 +116,6 @@ __device__ __forceinline__ uint64_t c4_desc(uint32_t addr, uint32_t lbo_bytes) {
   return d;
 }
 
-// one lane of the (converged) warp; always the same one, so that tcgen05.commit tracks the MMAs this lane issued
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void st_global_f32(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   uint64_t d;

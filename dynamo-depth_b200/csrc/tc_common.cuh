@@ -232,29 +232,43 @@ __device__ __forceinline__ void cta_teardown(const Cta& c, int mma_warp_id) {
 
 // ---- MMA issuer: called by the whole MMA warp; lane 0 issues -----------------------------------------
 // Tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; tile t reduces K blocks [kb0, kb1) of split t / tiles_mn.
+// one lane of the (converged) warp; always the same one, so that tcgen05.commit tracks the MMAs this lane issued
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 template <bool A_MN, bool B_MN, int BN>
 __device__ __forceinline__ void mma_issue_loop(const Cta& c, int total_tiles, int tiles_mn, int kb_per_split, int kb_total) {
   constexpr int B_TILE_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  if ((threadIdx.x & 31) == 0) {
-    // instruction descriptor: D fp32 (bits 4-5 = 1), A / B tf32 (bits 7-9, 10-12 = 2), major-ness (15, 16), N>>3 (17-22), M>>4 (24-28)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t stages = (uint32_t)c.stages;
-    uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int sp = tile / tiles_mn;
-      const int kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
-      const uint32_t buf = tcount & 1u, tph = (tcount >> 1) & 1u;
-      mbar_wait(c.tempty_bar + 8 * buf, tph ^ 1u);
+  // The whole warp runs the loop convergently (barrier waits, warp-uniform descriptor arithmetic); only the tcgen05
+  // instructions sit under elect.sync.  (Wrapping the loop in `if (lane == 0)` makes ptxas serialise every UTCHMMA behind an
+  // ELECT / BRA.U.ANY loop with R2UR moves -- measured ~100 clocks of issue per MMA in the convolution kernel.)
+  // instruction descriptor: D fp32 (bits 4-5 = 1), A / B tf32 (bits 7-9, 10-12 = 2), major-ness (15, 16), N>>3 (17-22), M>>4 (24-28)
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t stages = (uint32_t)c.stages;
+  uint32_t it = 0, tcount = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    const int sp = tile / tiles_mn;
+    const int kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+    const uint32_t buf = tcount & 1u, tph = (tcount >> 1) & 1u;
+    mbar_wait(c.tempty_bar + 8 * buf, tph ^ 1u);
+    tc_fence_after();
+    const uint32_t d_tmem = c.tmem_base + buf * 256u;
+    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+      const uint32_t stage = it % stages, ph = (it / stages) & 1u;
+      mbar_wait(c.full_bar + 8 * stage, ph);
       tc_fence_after();
-      const uint32_t d_tmem = c.tmem_base + buf * 256u;
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const uint32_t stage = it % stages, ph = (it / stages) & 1u;
-        mbar_wait(c.full_bar + 8 * stage, ph);
-        tc_fence_after();
-        const uint32_t a_hi = c.smem_base + stage * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-        const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+      const uint32_t a_hi = c.smem_base + stage * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+      const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint32_t oa = ks * (A_MN ? 1024u : 32u), ob = ks * (B_MN ? 1024u : 32u);
@@ -265,11 +279,15 @@ __device__ __forceinline__ void mma_issue_loop(const Cta& c, int total_tiles, in
           umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
         }
         tc_commit(c.empty_bar + 8 * stage);   // the stage may be refilled once these MMAs have read it
+        if (kb == kb1 - 1) tc_commit(c.tfull_bar + 8 * buf);       // accumulator complete
       }
-      tc_commit(c.tfull_bar + 8 * buf);       // accumulator complete
+      __syncwarp();
+    }
+    if (kb1 <= kb0) {   // (empty K range: still hand the accumulator over)
+      if (elect_one()) tc_commit(c.tfull_bar + 8 * buf);
+      __syncwarp();
     }
   }
-  __syncwarp();
 }
 
 // 32 TMEM lanes (this warp's quarter) x 32 consecutive columns -> r[0..31] of the lane's row
