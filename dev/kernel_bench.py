@@ -60,7 +60,8 @@ def bench_warp(B, reps, only=None):
         if only is not None and mode != only:
             continue
         batch, disps, Ts, flows, masks = warp_inputs(B, scales, mode, dev)
-        cfg = Fn.WarpConfig(scales=scales, cmpflow=mode >= 1, motmask=mode == 2, automask=automask)
+        cfg = Fn.WarpConfig(scales=scales, cmpflow=mode >= 1, motmask=mode == 2, automask=automask,
+                            keep_warped=os.environ.get("DD_BENCH_RECOMPUTE") is None)
         noises = [torch.randn(B, 2, H, W, device=dev) for _ in scales] if automask else None
         args = (cfg, batch[("color", 0, 0)], [batch[("color", -1, 0)], batch[("color", 1, 0)]], batch[("K", 0)], batch[("inv_K", 0)], Ts,
                 [batch[("ts", -1)], batch[("ts", 1)]], disps, flows, masks, noises)

@@ -74,3 +74,24 @@ def test_state_mismatch_and_missing_file(tmp_path):
         ckpt.apply_state(st, other, torch.optim.lr_scheduler.StepLR(other, 2, 0.5))
     with pytest.raises(FileNotFoundError):
         ckpt.load_state(str(tmp_path))
+
+
+def test_apply_state_refuses_a_different_parameter_order():
+    """Adam moments are stored by parameter index; a checkpoint written with another parameter order must be
+    refused instead of attaching the moments to the wrong tensors."""
+    import pytest
+    import torch
+    from dd_b200 import checkpoint as ckpt
+
+    a, b = torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(3))
+    opt = torch.optim.Adam([a, b], 1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 10, 0.5)
+    (a.sum() + 2 * b.sum()).backward()
+    opt.step()
+    state = ckpt.pack_state("disp_init", 0, 1, 1, opt, sched, [1, 1, 1, 1], with_rng=False,
+                            param_names=[("enc.a", (3,)), ("dec.b", (3,))])
+    opt2 = torch.optim.Adam([b, a], 1e-3)
+    sched2 = torch.optim.lr_scheduler.StepLR(opt2, 10, 0.5)
+    with pytest.raises(ValueError, match="parameter order"):
+        ckpt.apply_state(state, opt2, sched2, restore_rng=False, param_names=["dec.b", "enc.a"])
+    ckpt.apply_state(state, opt2, sched2, restore_rng=False, param_names=["enc.a", "dec.b"])   # same order: accepted
