@@ -31,8 +31,9 @@
 //                epilogue of tile 0 runs under the MMAs of tiles 1..T-1 and the next work item re-enters a tile's columns as
 //                soon as that tile has been read out.
 //   warps      : 0-3 producers (thread = patch positions; 8 coalesced channel loads, hi/lo split, 4 x 16-byte stores),
-//                4-7 epilogue (tcgen05.ld, bias / activation / residual / split stores through emit_output),
-//                8 MMA issuer (one thread), 9 weight loader (one thread)
+//                4-11 epilogue (tcgen05.ld, bias / activation / residual / split stores; two warps per TMEM lane quarter taking
+//                alternate 32-channel blocks -- the accumulators fill all 512 TMEM columns, so the epilogue of a tile is
+//                exposed until the tile is read out), 12 MMA issuer (one thread), 13 weight loader (one thread)
 #pragma once
 #include "tc_common.cuh"
 
@@ -42,8 +43,8 @@ constexpr int C4_KC = 8;          // input channels per K block (= K of one tf32
 constexpr int C4_PSTAGES = 3;     // patch ring
 constexpr int C4_WSTAGES = 2;     // weight ring
 constexpr int C4_PROD_THREADS = 128;
-constexpr int C4_EPI_WARP0 = 4, C4_MMA_WARP = 8, C4_W_WARP = 9;
-constexpr int C4_THREADS = 320;
+constexpr int C4_EPI_WARP0 = 4, C4_EPI_WARPS = 8, C4_MMA_WARP = 12, C4_W_WARP = 13;   // two epilogue warps per TMEM lane quarter
+constexpr int C4_THREADS = 448;
 constexpr int C4_MAX_COUT = 1024;  // bias staged in shared memory (n_tiles * BN floats)
 
 struct ConvTc4Args {
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < C4_WSTAGES; ++s) mbar_init(wfull + 8 * s, 1), mbar_init(wempty + 8 * s, 1);
     for (int s = 0; s < C4_PSTAGES; ++s) mbar_init(pfull + 8 * s, C4_PROD_THREADS), mbar_init(pempty + 8 * s, 1);
-    for (int s = 0; s < 4; ++s) mbar_init(tfull + 8 * s, 1), mbar_init(tempty + 8 * s, 4 * 32);
+    for (int s = 0; s < 4; ++s) mbar_init(tfull + 8 * s, 1), mbar_init(tempty + 8 * s, C4_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < g.n_tiles * BN + 32; i += C4_THREADS) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
@@ -332,8 +333,9 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: warp ew owns TMEM lanes 32 ew .. 32 ew + 31
-    const int ew = warp - C4_EPI_WARP0;
+    // ------------------------------------------------------------------ epilogue: warps with the same (warp & 3) = ew share TMEM
+    // lanes 32 ew .. 32 ew + 31 and take the 32-channel column blocks of their parity eh
+    const int ew = warp & 3, eh = (warp - C4_EPI_WARP0) >> 2;
     const size_t HoWo = (size_t)a.Ho * a.Wo;
     uint32_t tcount = 0;
     for (int work = blockIdx.x; work < g.total_work; work += gridDim.x, ++tcount) {
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
         const bool valid = c >= 1 && c <= cols_out && y < a.Ho && x < a.Wo;
         const size_t pix = (size_t)y * a.Wo + x;
 #pragma unroll 1
-        for (int cb = 0; cb < ((g.debug & 4) ? 0 : (BN + 31) / 32); ++cb) {
+        for (int cb = eh; cb < ((g.debug & 4) ? 0 : (BN + 31) / 32); cb += 2) {
           const int co0 = nt * BN + cb * 32;
           if (co0 >= a.Cout) break;   // warp-uniform
           // Loads first, stores last: the output pointers are generic, so the compiler must assume that a store may alias
@@ -371,9 +373,17 @@ __global__ void __launch_bounds__(C4_THREADS, 1) conv_tc4_kernel(const __grid_co
               v[4 * j4 + 3] = (__uint_as_float(rm[4 * j4 + 3]) + __uint_as_float(rc[4 * j4 + 3])) + b4.w;
             }
           }
-          if (a.act != DD_ACT_NONE) {
+          // activations with the hardware exponential (ex2.approx: absolute error <= ~1.5e-7 on these ranges, far inside the
+          // 1e-4 parity bound; the IEEE expf costs ~20 instructions per element on an epilogue that is not hidden)
+          if (a.act == DD_ACT_ELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : __expf(v[j]) - 1.f;
+          } else if (a.act == DD_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (a.act == DD_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
           }
           // destination of channel co: `out` (C_a channels) below the split, `out1` (Cout - split channels) from it on
           const int C_a = a.split > 0 ? a.split : a.Cout;
