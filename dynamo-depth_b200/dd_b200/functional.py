@@ -777,3 +777,58 @@ class _BlockTailFn(torch.autograd.Function):
 def block_tail(x, y, gamma=None, scale=None):
     """x + (scale[:, None, None, None] * gamma * y).permute(0, 3, 1, 2) with y in (B,H,W,C); scale is not differentiated."""
     return _BlockTailFn.apply(x, y, gamma, scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# training-mode BatchNorm2d (+ exact GELU) of the Lite-Mono encoder (networks/depth_encoder.py:113-122, :194/:208)
+# ---------------------------------------------------------------------------------------------
+class _BatchNormGeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, gelu):
+        x, weight, bias = _prep(x), _prep(weight), _prep(bias)
+        B, C, H, W = x.shape
+        lib = L.load()
+        y = torch.empty_like(x)
+        stats = torch.empty((2, C), device=x.device, dtype=torch.float32)
+        ws = _workspace(lib.dd_bn_workspace_bytes(C), x.device)
+        L.check(lib.dd_bn_gelu_fwd(L.ptr(x), B, C, H * W, L.ptr(weight), L.ptr(bias), float(eps), float(momentum), int(gelu), L.ptr(y),
+                                   L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(running_mean), L.ptr(running_var), L.ptr(ws), ws.numel(),
+                                   _stream()), "dd_bn_gelu_fwd")
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.gelu = int(gelu)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, bias, stats = ctx.saved_tensors
+        B, C, H, W = x.shape
+        g = _prep(g)
+        lib = L.load()
+        need_x = ctx.needs_input_grad[0]
+        need_w = weight is not None and ctx.needs_input_grad[1]
+        need_b = bias is not None and ctx.needs_input_grad[2]
+        if not (need_x or need_w or need_b):
+            return (None,) * 8
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.empty_like(weight) if need_w else None
+        gb = torch.empty_like(bias) if need_b else None
+        ws = _workspace(lib.dd_bn_workspace_bytes(C), x.device)
+        L.check(lib.dd_bn_gelu_bwd(L.ptr(x), L.ptr(g), B, C, H * W, L.ptr(weight), L.ptr(bias), L.ptr(stats[0]), L.ptr(stats[1]),
+                                   ctx.gelu, L.ptr(gx), L.ptr(gw), L.ptr(gb), L.ptr(ws), ws.numel(), _stream()), "dd_bn_gelu_bwd")
+        return gx, gw, gb, None, None, None, None, None
+
+
+def batch_norm_gelu(x, bn, gelu=False):
+    """`gelu(bn(x))` (or `bn(x)`) for an nn.BatchNorm2d in training mode on an NCHW CUDA tensor as two streaming passes
+    (csrc/batchnorm.cu); running statistics and num_batches_tracked are updated exactly as nn.BatchNorm2d.forward does.
+    Eval mode (running statistics) and modules without batch statistics stay on torch."""
+    if not bn.training or not bn.track_running_stats or x.dim() != 4:
+        y = bn(x)
+        return torch.nn.functional.gelu(y) if gelu else y
+    momentum = bn.momentum
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:   # cumulative moving average
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return _BatchNormGeluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, 0.0 if momentum is None else momentum,
+                                  bn.eps, gelu)

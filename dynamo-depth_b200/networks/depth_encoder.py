@@ -160,6 +160,9 @@ class BNGELU(nn.Module):
         self.act = nn.GELU()
 
     def forward(self, x):
+        if _fused(x):   # training-mode statistics + affine + GELU as two streaming passes (csrc/batchnorm.cu)
+            from dd_b200 import functional as DF
+            return DF.batch_norm_gelu(x, self.bn, gelu=True)
         return self.act(self.bn(x))
 
 
@@ -223,7 +226,7 @@ class DilatedConv(nn.Module):
     def forward(self, x):
         if _fused(x):
             from dd_b200 import functional as DF
-            y = DF.nchw_to_nhwc(self.bn1(self.ddwconv(x)))
+            y = DF.nchw_to_nhwc(DF.batch_norm_gelu(self.ddwconv(x), self.bn1))
             return _block_tail(self, x, self.pwconv2(self.act(self.pwconv1(y))))
         y = self.bn1(self.ddwconv(x)).permute(0, 2, 3, 1)
         y = _mlp_branch(self, y).permute(0, 3, 1, 2)

@@ -290,6 +290,26 @@ int dd_block_tail_fwd(const float* x, const float* y, const float* gamma, const 
 int dd_block_tail_bwd(const float* grad_out, const float* y, const float* gamma, const float* scale, int B, int C, int HW,
                       float* grad_y, float* grad_gamma, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm2d (+ exact GELU) of the Lite-Mono encoder over NCHW fp32 tensors (csrc/batchnorm.cu):
+ * networks/depth_encoder.py:113-122 `BNGELU` (nn.BatchNorm2d(eps=1e-5) -> nn.GELU()) of the stem convolutions :131-145 and
+ * `DilatedConv.bn1` :194,:208.  x, y, grad_y, grad_x are (B,C,HW); gamma / beta (C) may be NULL (= 1 / 0).
+ *   dd_bn_gelu_fwd : batch statistics over (B,HW) per channel (biased variance), y = [gelu]((x - mean) * invstd * gamma + beta);
+ *                    save_mean / save_invstd (C) are written for the backward pass; running_mean / running_var (may be NULL)
+ *                    are updated in place as nn.BatchNorm2d does: r = (1 - momentum) * r + momentum * stat, with the
+ *                    unbiased variance
+ *   dd_bn_gelu_bwd : grad_x (may be NULL), grad_gamma, grad_beta (may be NULL) from x, grad_y and the saved statistics;
+ *                    with gelu != 0 grad_y is the gradient w.r.t. the GELU output (the BN output is re-derived from x)
+ * Both need dd_bn_workspace_bytes(C) bytes of workspace (per-CTA partial sums; deterministic reduction, no atomics).
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_bn_workspace_bytes(int C);
+int dd_bn_gelu_fwd(const float* x, int B, int C, int HW, const float* gamma, const float* beta, float eps, float momentum, int gelu,
+                   float* y, float* save_mean, float* save_invstd, float* running_mean, float* running_var, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int dd_bn_gelu_bwd(const float* x, const float* grad_y, int B, int C, int HW, const float* gamma, const float* beta,
+                   const float* save_mean, const float* save_invstd, int gelu, float* grad_x, float* grad_gamma, float* grad_beta,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
