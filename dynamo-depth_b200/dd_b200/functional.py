@@ -832,3 +832,46 @@ def batch_norm_gelu(x, bn, gelu=False):
             momentum = 1.0 / float(bn.num_batches_tracked)
     return _BatchNormGeluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, 0.0 if momentum is None else momentum,
                                   bn.eps, gelu)
+
+
+# ---------------------------------------------------------------------------------------------
+# channels_last LayerNorm of the LGFI blocks (networks/depth_encoder.py:90-104)
+# ---------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x, weight, bias = _prep(x), _prep(weight), _prep(bias)
+        C_ = x.shape[-1]
+        M = x.numel() // C_
+        y = torch.empty_like(x)
+        stats = torch.empty((2, M), device=x.device, dtype=torch.float32)
+        L.check(L.load().dd_layernorm_fwd(L.ptr(x), M, C_, L.ptr(weight), L.ptr(bias), float(eps), L.ptr(y), L.ptr(stats[0]),
+                                          L.ptr(stats[1]), _stream()), "dd_layernorm_fwd")
+        ctx.save_for_backward(x, weight, stats)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, stats = ctx.saved_tensors
+        C_ = x.shape[-1]
+        M = x.numel() // C_
+        g = _prep(g)
+        lib = L.load()
+        need_x = ctx.needs_input_grad[0]
+        need_w = weight is not None and ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if not (need_x or need_w or need_b):
+            return None, None, None, None
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.empty(C_, device=x.device, dtype=torch.float32) if need_w else None
+        gb = torch.empty(C_, device=x.device, dtype=torch.float32) if need_b else None
+        ws = _workspace(lib.dd_layernorm_workspace_bytes(C_), x.device) if (need_w or need_b) else None
+        L.check(lib.dd_layernorm_bwd(L.ptr(x), L.ptr(g), M, C_, L.ptr(weight), L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gx), L.ptr(gw),
+                                     L.ptr(gb), L.ptr(ws), ws.numel() if ws is not None else 0, _stream()), "dd_layernorm_bwd")
+        return gx, gw, gb, None
+
+
+def layer_norm(x, weight=None, bias=None, eps=1e-6):
+    """F.layer_norm(x, (C,), weight, bias, eps) over the last dimension of a CUDA tensor, C a multiple of 4 and <= 512."""
+    return _LayerNormFn.apply(x, weight, bias, eps)

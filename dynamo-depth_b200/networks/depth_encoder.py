@@ -102,6 +102,9 @@ class LayerNorm(nn.Module):
 
     def forward(self, x):
         if self.data_format == "channels_last":
+            if x.is_cuda and EncoderLinear.mode != "torch" and x.shape[-1] % 4 == 0 and x.shape[-1] <= 512:
+                from dd_b200 import functional as DF   # row-per-sub-warp kernel (csrc/layernorm.cu)
+                return DF.layer_norm(x, self.weight, self.bias, self.eps)
             return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
         mu = x.mean(1, keepdim=True)
         var = (x - mu).pow(2).mean(1, keepdim=True)

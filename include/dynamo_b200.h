@@ -310,6 +310,21 @@ int dd_bn_gelu_bwd(const float* x, const float* grad_y, int B, int C, int HW, co
                    const float* save_mean, const float* save_invstd, int gelu, float* grad_x, float* grad_gamma, float* grad_beta,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * channels_last LayerNorm of the Lite-Mono LGFI blocks (csrc/layernorm.cu): networks/depth_encoder.py:90-104
+ * `LayerNorm.forward` -> F.layer_norm over the last dimension (:261 norm_xca, :266 norm).  x, y, grad_y, grad_x are (M, C)
+ * row-major, C a multiple of 4 and <= 512; gamma / beta (C) may be NULL (= 1 / 0); all pointers 16-byte aligned.
+ *   dd_layernorm_fwd : y = (x - mean_row) * rstd_row * gamma + beta with the biased row variance; mean / rstd (M) are kept
+ *                      for the backward pass
+ *   dd_layernorm_bwd : grad_x (may be NULL), grad_gamma, grad_beta (may be NULL; they need
+ *                      dd_layernorm_workspace_bytes(C) bytes of workspace: per-CTA partials, fixed-order reduction)
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_layernorm_workspace_bytes(int C);
+int dd_layernorm_fwd(const float* x, long long M, int C, const float* gamma, const float* beta, float eps, float* y, float* mean,
+                     float* rstd, void* stream);
+int dd_layernorm_bwd(const float* x, const float* grad_y, long long M, int C, const float* gamma, const float* mean, const float* rstd,
+                     float* grad_x, float* grad_gamma, float* grad_beta, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
