@@ -129,6 +129,11 @@ SIGNATURES = {
     "dd_layernorm_workspace_bytes": (C.c_size_t, [C.c_int]),
     "dd_layernorm_fwd": (C.c_int, [FP, C.c_longlong, C.c_int, FP, FP, C.c_float, FP, FP, FP, FP]),
     "dd_layernorm_bwd": (C.c_int, [FP, FP, C.c_longlong, C.c_int, FP, FP, FP, FP, FP, FP, FP, C.c_size_t, FP]),
+    "dd_dwconv3x3_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "dd_dwconv3x3_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_dwconv3x3_wgrad": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, C.c_size_t, FP]),
+    "dd_maxpool3x3s2_nhwc_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
+    "dd_maxpool3x3s2_nhwc_bwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_bn_workspace_bytes": (C.c_size_t, [C.c_int]),
     "dd_bn_gelu_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, FP, FP, FP, FP, FP, FP,
                                  C.c_size_t, FP]),

@@ -875,3 +875,86 @@ class _LayerNormFn(torch.autograd.Function):
 def layer_norm(x, weight=None, bias=None, eps=1e-6):
     """F.layer_norm(x, (C,), weight, bias, eps) over the last dimension of a CUDA tensor, C a multiple of 4 and <= 512."""
     return _LayerNormFn.apply(x, weight, bias, eps)
+
+
+# ---------------------------------------------------------------------------------------------
+# depth-wise dilated 3x3 convolution of the DilatedConv blocks (networks/depth_encoder.py:148-168)
+# ---------------------------------------------------------------------------------------------
+DWCONV_DILATIONS = (1, 2, 3, 4, 6)
+
+
+class _DwConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, dilation):
+        x, weight = _prep(x), _prep(weight)
+        B, C_, H, W = x.shape
+        if tuple(weight.shape) != (C_, 1, 3, 3):
+            raise L.DynamoB200Error(f"dwconv3x3: weight {tuple(weight.shape)} does not match {C_} channels")
+        y = torch.empty_like(x)
+        L.check(L.load().dd_dwconv3x3_fwd(L.ptr(x), L.ptr(weight), B, C_, H, W, int(dilation), 0, L.ptr(y), _stream()), "dd_dwconv3x3_fwd")
+        ctx.save_for_backward(x, weight)
+        ctx.dilation = int(dilation)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        B, C_, H, W = x.shape
+        g = _prep(g)
+        lib = L.load()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            L.check(lib.dd_dwconv3x3_fwd(L.ptr(g), L.ptr(weight), B, C_, H, W, ctx.dilation, 1, L.ptr(gx), _stream()), "dd_dwconv3x3_fwd")
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(weight)
+            ws = _workspace(lib.dd_dwconv3x3_workspace_bytes(C_), x.device)
+            L.check(lib.dd_dwconv3x3_wgrad(L.ptr(x), L.ptr(g), B, C_, H, W, ctx.dilation, L.ptr(gw), L.ptr(ws), ws.numel(), _stream()),
+                    "dd_dwconv3x3_wgrad")
+        return gx, gw, None
+
+
+def dwconv3x3(x, weight, dilation=1):
+    """F.conv2d(x, weight, None, 1, dilation, dilation, groups=C) for a (C,1,3,3) weight on an NCHW CUDA tensor (W % 4 == 0)."""
+    return _DwConvFn.apply(x, weight, dilation)
+
+
+# ---------------------------------------------------------------------------------------------
+# nn.MaxPool2d(3, 2, 1) of the ResNet trunks on channels_last activations (networks/resnet_encoder.py:18,:130)
+# ---------------------------------------------------------------------------------------------
+def _nhwc_ptr(t):
+    """Device pointer of a 4-D fp32 CUDA tensor that is dense in channels_last order."""
+    if not t.is_cuda:
+        raise L.DynamoB200Error("dynamo_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous(memory_format=torch.channels_last):
+        raise L.DynamoB200Error("maxpool3x3s2: expected a channels_last fp32 (B,C,H,W) tensor")
+    return t.data_ptr()
+
+
+class _MaxPoolNHWCFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        if x.is_cuda and x.dim() == 4:
+            x = x.float().contiguous(memory_format=torch.channels_last)
+        B, C_, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((B, C_, Ho, Wo), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        arg = torch.empty((B, Ho, Wo, C_), device=x.device, dtype=torch.uint8)
+        L.check(L.load().dd_maxpool3x3s2_nhwc_fwd(_nhwc_ptr(x), B, H, W, C_, _nhwc_ptr(y), L.ptr(arg), _stream()), "dd_maxpool3x3s2_nhwc_fwd")
+        ctx.save_for_backward(arg)
+        ctx.dims = (B, C_, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        B, C_, H, W = ctx.dims
+        g = g.float().contiguous(memory_format=torch.channels_last)
+        gx = torch.empty((B, C_, H, W), device=g.device, dtype=torch.float32, memory_format=torch.channels_last)
+        L.check(L.load().dd_maxpool3x3s2_nhwc_bwd(_nhwc_ptr(g), L.ptr(arg), B, H, W, C_, _nhwc_ptr(gx), _stream()), "dd_maxpool3x3s2_nhwc_bwd")
+        return gx
+
+
+def maxpool3x3s2(x):
+    """F.max_pool2d(x, 3, 2, 1) on a channels_last CUDA tensor (C % 4 == 0); the result is channels_last as well."""
+    return _MaxPoolNHWCFn.apply(x)

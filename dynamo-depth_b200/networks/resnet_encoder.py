@@ -70,7 +70,11 @@ class ResnetEncoder(nn.Module):
             input_image = input_image.contiguous(memory_format=torch.channels_last)
         x = e.relu(e.bn1(e.conv1((input_image - 0.45) / 0.225)))
         self.features = [x]
-        x = e.layer1(e.maxpool(x))
+        if self.channels_last and x.is_cuda and x.shape[1] % 4 == 0 and (e.maxpool.kernel_size, e.maxpool.stride, e.maxpool.padding) == (3, 2, 1):
+            from dd_b200 import functional as DF   # gather-style NHWC max-pool (csrc/pool.cu)
+            x = e.layer1(DF.maxpool3x3s2(x))
+        else:
+            x = e.layer1(e.maxpool(x))
         self.features.append(x)
         for layer in (e.layer2, e.layer3, e.layer4):
             x = layer(x)

@@ -325,6 +325,30 @@ int dd_layernorm_fwd(const float* x, long long M, int C, const float* gamma, con
 int dd_layernorm_bwd(const float* x, const float* grad_y, long long M, int C, const float* gamma, const float* mean, const float* rstd,
                      float* grad_x, float* grad_gamma, float* grad_beta, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Depth-wise dilated 3x3 convolution of the Lite-Mono DilatedConv blocks (csrc/dwconv.cu): networks/depth_encoder.py:148-168
+ * `CDilated` = nn.Conv2d(dim, dim, 3, stride=1, padding=d, dilation=d, groups=dim, bias=False) as used at :193/:207.
+ * x, y, grad_y are (B,C,H,W) NCHW with W a multiple of 4, w is (C,1,3,3); dilation in {1, 2, 3, 4, 6}.
+ *   dd_dwconv3x3_fwd   : y = conv(x, w); flip != 0 applies the taps mirrored, i.e. computes the data gradient when called
+ *                        on grad_y
+ *   dd_dwconv3x3_wgrad : grad_w (C,1,3,3) from x and grad_y; needs dd_dwconv3x3_workspace_bytes(C) bytes (per-CTA partials,
+ *                        fixed-order reduction)
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_dwconv3x3_workspace_bytes(int C);
+int dd_dwconv3x3_fwd(const float* x, const float* w, int B, int C, int H, int W, int dilation, int flip, float* y, void* stream);
+int dd_dwconv3x3_wgrad(const float* x, const float* grad_y, int B, int C, int H, int W, int dilation, float* grad_w, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet trunks (csrc/pool.cu): networks/resnet_encoder.py:18,:130,
+ * on channels_last activations, i.e. x is (B,H,W,C) and y (B,Ho,Wo,C) in memory, Ho = (H-1)/2 + 1, C a multiple of 4.
+ *   dd_maxpool3x3s2_nhwc_fwd : y and argmax (B,Ho,Wo,C bytes: position 0..8 of the maximum inside its window, first
+ *                              maximum in scan order, NaN propagates -- the rule of ATen's kernel)
+ *   dd_maxpool3x3s2_nhwc_bwd : grad_x (B,H,W,C) gathered from grad_y and argmax (every element written once; no atomics)
+ * ------------------------------------------------------------------------------------------ */
+int dd_maxpool3x3s2_nhwc_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* argmax, void* stream);
+int dd_maxpool3x3s2_nhwc_bwd(const float* grad_y, const unsigned char* argmax, int B, int H, int W, int C, float* grad_x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
