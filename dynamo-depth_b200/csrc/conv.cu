@@ -1256,6 +1256,7 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __rest
 }  // namespace dd
 
 #include "conv_wgrad_tc.cuh"  // tcgen05 weight gradient of the 3x3 layers (uses VirtIn, conv_tc4.cuh helpers)
+#include "conv_pw_small.cuh"  // 1x1 layers with <= 4 output channels as 16-byte streams (uses ConvArgs, VirtIn, apply_act)
 
 namespace dd {
 
@@ -1332,6 +1333,8 @@ static bool use_winograd(int ks, int cin, int cout) {
 
 static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose,
                     cudaStream_t st) {
+  if (use_pw_small(ks, transpose ? args.Cin : args.Cout, args.Ho, args.Wo, args.vin.up0))   // motion-decoder 1x1 reductions
+    return transpose ? run_pw_small_dgrad(args, w_oihw, st) : run_pw_small_fwd(args, w_oihw, st);
   if (use_tc4_conv(ks, args.Cin, args.Cout))  // tensor cores (3xTF32, fp32 accuracy): every 3x3 layer with more than 16 output channels
     return run_conv_tc4(args, wt_buf, w_oihw, Cout_f, Cin_f, transpose, device_sms(), st);
   if (use_winograd(ks, args.Cin, args.Cout)) {
@@ -1436,6 +1439,7 @@ static ConvWs conv_ws(const dd_conv_desc* d) {
   w.gpad = w.wtd + align256(wt_d);
   w.slabs = w.gpad + align256((size_t)d->B * Cin * Hp * Wp * sizeof(float));
   w.total = w.slabs + (use_tc_wgrad(d->ksize, Cin, d->Cout) ? align256(conv_wgrad_tc_slab_bytes(d->B, d->H, d->W, Cin, d->Cout, device_sms())) : 0);
+  if (use_pw_small(d->ksize, d->Cout, d->H, d->W, d->up0)) w.total = w.slabs + align256(pw_small_wgrad_bytes(d->B, d->H, d->W, Cin));
   return w;
 }
 
@@ -1496,6 +1500,9 @@ int conv_bwd_impl(const dd_conv_desc* d, const float* out, const float* grad_out
     wt.slabs = reinterpret_cast<float*>((char*)workspace + ws.slabs);
     wt.gb = grad_bias;
     rc = run_conv_wgrad_tc(wt, grad_weight, device_sms(), st);
+    if (rc != DD_OK) return rc;
+  } else if (grad_weight && use_pw_small(d->ksize, d->Cout, d->H, d->W, d->up0)) {
+    rc = run_pw_small_wgrad(make_vin(d), g, d->B, d->H, d->W, Cin, d->Cout, reinterpret_cast<float*>((char*)workspace + ws.slabs), grad_weight, st);
     if (rc != DD_OK) return rc;
   } else if (grad_weight) {
     DD_CHECK_CUDA(cudaMemsetAsync(grad_weight, 0, (size_t)d->Cout * Cin * KK * sizeof(float), st));

@@ -43,6 +43,10 @@ CASES = [
     (2, 3, 9, 9, 10, 18, 3, "zero", "none", "none", False),       # few output channels, width not a multiple of 4
     (1, 5, 0, 12, 7, 9, 3, "reflect", "elu", "none", False),      # odd sizes, reflection inside a partial tile
     (2, 20, 0, 3, 34, 70, 3, "zero", "none", "none", True),       # several tiles, residual, 3 outputs
+    (2, 9, 9, 1, 20, 36, 1, "zero", "none", "none", True),        # 1x1 mask reduction: one output, odd channel counts
+    (1, 33, 33, 3, 96, 176, 1, "zero", "none", "none", True),     # 1x1 reduction over several weight-gradient chunks per image
+    (2, 128, 0, 4, 6, 22, 1, "zero", "sigmoid", "none", False),   # 1x1, four outputs, activation, partial pixel block
+    (2, 16, 16, 3, 5, 7, 1, "zero", "none", "none", True),        # 1x1, H*W not a multiple of 4: generic core
 ]
 
 
