@@ -327,6 +327,12 @@ def run_ours(args):
         timed(resident, 1, False)
         torch.cuda.profiler.stop()
         return
+    if args.trace_step:     # torch.profiler timeline of two steps: where the GPU waits for the host (dev/gap_report.py reads it)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            timed(resident, 2, False)
+        prof.export_chrome_trace(args.trace_step)
+        return
     Fn.KERNEL_TIMERS = {}
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -507,6 +513,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip variants.eager_b200 (the reference in eager PyTorch on this GPU)")
     ap.add_argument("--no-variants", action="store_true", help="skip every variant measurement")
+    ap.add_argument("--trace-step", default=None, help="write a torch.profiler chrome trace of two steps to this path, no JSON line")
     ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around one step (for ncu), no JSON line")
     args = ap.parse_args()
     if args.impl == "reference":

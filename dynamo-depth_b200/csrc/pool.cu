@@ -59,22 +59,28 @@ __global__ void __launch_bounds__(MP_THREADS) maxpool_bwd_kernel(const float4* _
     t /= W;
     const int iy = (int)(t % H), b = (int)(t / H);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    // windows covering (iy, ix): oy with 2 oy - 1 <= iy <= 2 oy + 1
+    // windows covering (iy, ix): oy with 2 oy - 1 <= iy <= 2 oy + 1, i.e. iy >> 1 and (iy + 1) >> 1 (the same window for even
+    // iy); all candidate loads are issued before any is used
     const int oy0 = iy >> 1, oy1 = (iy + 1) >> 1, ox0 = ix >> 1, ox1 = (ix + 1) >> 1;
-    for (int oy = oy0; oy <= oy1; ++oy) {
-      if (oy >= Ho) continue;
-      const int ky = iy - (2 * oy - 1);
-      for (int ox = ox0; ox <= ox1; ++ox) {
-        if (ox >= Wo) continue;
-        const int code = ky * 3 + (ix - (2 * ox - 1));
-        const long long o = (((long long)b * Ho + oy) * Wo + ox) * C4 + c;
-        const uchar4 sel = __ldg(idx + o);
-        const float4 g = __ldg(gy + o);
-        if (sel.x == code) acc.x += g.x;
-        if (sel.y == code) acc.y += g.y;
-        if (sel.z == code) acc.z += g.z;
-        if (sel.w == code) acc.w += g.w;
-      }
+    const int oys[2] = {oy0, oy1}, oxs[2] = {ox0, ox1};
+    uchar4 sel[4];
+    float4 g[4];
+    int code[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int oy = oys[k >> 1], ox = oxs[k & 1];
+      const bool ok = oy < Ho && ox < Wo && !((k >> 1) == 1 && oy1 == oy0) && !((k & 1) == 1 && ox1 == ox0);
+      code[k] = ok ? (iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)) : 255;
+      const long long o = (((long long)b * Ho + min(oy, Ho - 1)) * Wo + min(ox, Wo - 1)) * C4 + c;
+      sel[k] = __ldg(idx + o);
+      g[k] = __ldg(gy + o);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (sel[k].x == code[k]) acc.x += g[k].x;
+      if (sel[k].y == code[k]) acc.y += g[k].y;
+      if (sel[k].z == code[k]) acc.z += g[k].z;
+      if (sel[k].w == code[k]) acc.w += g[k].w;
     }
     gx[u] = acc;
   }

@@ -333,10 +333,16 @@ def smooth_sums(inps, imgs, norms):
     return _SmoothFn.apply(tuple(bool(x) for x in norms), n, *[_prep(x) for x in inps], *[_prep(x) for x in imgs])
 
 
+_SMOOTH_DEN = {}
+
+
 def smooth_means(sums, shapes):
     """(n,2) sums -> per-task  mean_x + mean_y  (tools.py:326) as an (n,) tensor."""
-    den = torch.tensor([[B * Cc * h * (w - 1), B * Cc * (h - 1) * w] for (B, Cc, h, w) in shapes], dtype=torch.float32,
-                       device=sums.device)
+    key = (tuple(tuple(int(v) for v in sh) for sh in shapes), str(sums.device))
+    den = _SMOOTH_DEN.get(key)
+    if den is None:   # built once per shape set: torch.tensor(list, device=cuda) is a pageable copy that blocks the host
+        den = _SMOOTH_DEN[key] = torch.tensor([[B * Cc * h * (w - 1), B * Cc * (h - 1) * w] for (B, Cc, h, w) in shapes],
+                                              dtype=torch.float32).to(sums.device)
     return (sums / den).sum(1)
 
 

@@ -138,17 +138,42 @@ class GroundPlane(nn.Module):
         A, rhs = self._design(pts)
         return A @ param - rhs
 
+    _PIN_SLOTS = 8
+
+    def _stage_indices(self, idx_np, device):
+        """Host RNG draw -> device without a host synchronisation: a small ring of pinned buffers and non-blocking copies
+        (a pageable cudaMemcpy blocks the host until the GPU reaches it, i.e. once per scale in the middle of the step);
+        a slot is reused only after the copy issued from it has completed."""
+        ring = self.__dict__.setdefault("_pin_ring", {})
+        key = (tuple(idx_np.shape), str(device))
+        slots = ring.get(key)
+        if slots is None:
+            slots = ring[key] = {"next": 0, "bufs": [torch.empty(idx_np.shape, dtype=torch.int64, pin_memory=True) for _ in range(self._PIN_SLOTS)],
+                                 "events": [None] * self._PIN_SLOTS}
+        i = slots["next"]
+        slots["next"] = (i + 1) % self._PIN_SLOTS
+        if slots["events"][i] is not None:
+            slots["events"][i].synchronize()
+        slots["bufs"][i].numpy()[...] = idx_np
+        out = slots["bufs"][i].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        slots["events"][i] = ev
+        return out
+
     def estimate_ground_plane_fused(self, points, row0):
         """points (B,3,H,W) on the GPU; same result as estimate_ground_plane on points[:, :, row0:, :]."""
         B, _, H, W = points.shape
         N = (H - row0) * W
         k = self.num_points_per_it * self.max_it
         flat = points[:, :, row0:, :].reshape(B, 3, N)
-        idx = torch.from_numpy(np.stack([np.asarray(self.rand_index_fn(N, k)) for _ in range(B)])).to(points.device)
+        idx = self._stage_indices(np.stack([np.asarray(self.rand_index_fn(N, k)) for _ in range(B)]), points.device)
         picks = torch.gather(flat, 2, idx.unsqueeze(1).expand(B, 3, k)).permute(0, 2, 1)        # (B, k, 3)
         A, rhs = self._design(picks.reshape(-1, self.num_points_per_it, 3))
         At = A.transpose(2, 1)
-        ws = (torch.inverse(At @ A + 1e-6) @ At @ rhs).reshape(-1, 3)                          # (B*max_it, 3)
+        # inv_ex: the same LU-based inverse as torch.inverse (tools.py:124) without its device -> host error check, which
+        # would stall the host in the middle of every step
+        ws = (torch.linalg.inv_ex(At @ A + 1e-6).inverse @ At @ rhs).reshape(-1, 3)            # (B*max_it, 3)
         counts = _F.ground_score(points, ws, row0, self.tol).reshape(B, self.max_it)
         best = counts.argmax(1)
         return ws.reshape(B, self.max_it, 3, 1)[torch.arange(B, device=points.device), best]
