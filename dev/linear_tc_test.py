@@ -64,10 +64,11 @@ def bench(M, K, N, reps=10):
         return e0.elapsed_time(e1) / reps
 
     P = Fn.L.ptr
+    ws = torch.empty(lib.dd_linear_workspace_bytes(M, K, N), dtype=torch.uint8, device="cuda")
     res = {
-        "fwd": t(lambda: lib.dd_linear_fwd(P(x), P(w), P(b), M, K, N, P(y), st)),
-        "dx": t(lambda: lib.dd_linear_bwd(P(x), P(w), P(gy), M, K, N, P(gx), None, None, st)),
-        "dw": t(lambda: lib.dd_linear_bwd(P(x), P(w), P(gy), M, K, N, None, P(gw), P(gb), st)),
+        "fwd": t(lambda: lib.dd_linear_fwd(P(x), P(w), P(b), M, K, N, P(y), P(ws), ws.numel(), st)),
+        "dx": t(lambda: lib.dd_linear_bwd(P(x), P(w), P(gy), M, K, N, P(gx), None, None, P(ws), ws.numel(), st)),
+        "dw": t(lambda: lib.dd_linear_bwd(P(x), P(w), P(gy), M, K, N, None, P(gw), P(gb), P(ws), ws.numel(), st)),
         "t32_fwd": t(lambda: torch.nn.functional.linear(x, w, b)),
         "t32_dx": t(lambda: gy @ w),
         "t32_dw": t(lambda: gy.t() @ x),

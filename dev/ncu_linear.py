@@ -19,6 +19,7 @@ for (M, K, N) in [(245760, 64, 384), (15360, 1344, 224)]:
     gw = torch.empty(N, K, device="cuda")
     gb = torch.empty(N, device="cuda")
     st = Fn._stream()
-    lib.dd_linear_fwd(P(x), P(w), P(b), M, K, N, P(y), st)
-    lib.dd_linear_bwd(P(x), P(w), P(gy), M, K, N, P(gx), P(gw), P(gb), st)
+    ws = torch.empty(lib.dd_linear_workspace_bytes(M, K, N), dtype=torch.uint8, device="cuda")
+    lib.dd_linear_fwd(P(x), P(w), P(b), M, K, N, P(y), P(ws), ws.numel(), st)
+    lib.dd_linear_bwd(P(x), P(w), P(gy), M, K, N, P(gx), P(gw), P(gb), P(ws), ws.numel(), st)
     torch.cuda.synchronize()

@@ -39,18 +39,45 @@ struct GemmArgs {
   const float* A;
   const float* B;
   float* C;
+  const float* Bpre;     // B_PRE kernels: B already split into (hi, lo) tile images [n tile][K block][hi | lo] (linear_prep_b_kernel)
   const float* bias;     // (Nc) added to every row, or NULL
   float* colsum;         // weight-gradient mode: (Mc) sums of A over the reduction (bias gradient), or NULL
   long long lda, ldb, ldc;
   int Mc, Nc, Kr;
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
   int stages, atomic;
+  int debug;             // DD_LINEAR_DEBUG ablations (timing experiments only): 1 = no global stores in the epilogue, 2 = no A loads
 };
 
 template <int NB32>
 __host__ __device__ constexpr int linear_groups() { return groups_for(stages_for(2 * A_TILE_BYTES + 2 * NB32 * 32 * BK * 4)); }
 
-template <bool A_MN, bool B_MN, int NB32>
+// B operand of the forward / input-gradient contractions = the layer's weight: the same few tiles for every one of the
+// M / 128 row tiles.  Splitting them in the producers cost more instructions than the activations themselves (12 of the 20
+// 16-byte chunks per thread and K block at BN = 192), so they are split ONCE per call into the exact shared-memory image of
+// a stage (hi tile | lo tile, swizzled as store_tile writes it) and arrive by one cp.async.bulk per K block.
+template <bool B_MN, int NB32>
+__global__ void __launch_bounds__(GROUP_THREADS) linear_prep_b_kernel(const float* __restrict__ B, long long ldb, int Nc, int Kr, int kb_total,
+                                                                      float* __restrict__ dst) {
+  constexpr int BN = NB32 * 32;
+  constexpr int B_TILE_BYTES = BN * BK * 4;
+  constexpr int B_F4 = BN * BK / 4 / GROUP_THREADS;
+  const int kb = blockIdx.x, nt = blockIdx.y;
+  TileMap<B_MN, BN> mb;
+  mb.init(threadIdx.x);
+  float4 vb[B_F4];
+  load_tile<B_MN, BN, B_F4>(vb, mb, B, ldb, nt * BN, Nc, kb * BK, Kr);
+  char* img = reinterpret_cast<char*>(dst) + ((size_t)nt * kb_total + kb) * 2 * B_TILE_BYTES;
+#pragma unroll
+  for (int i = 0; i < B_F4; ++i) {
+    const uint32_t o = mb.soff_t + TileMap<B_MN, BN>::s_step(i);
+    const float hx = tf32_rn(vb[i].x), hy = tf32_rn(vb[i].y), hz = tf32_rn(vb[i].z), hw = tf32_rn(vb[i].w);
+    *reinterpret_cast<float4*>(img + o) = make_float4(hx, hy, hz, hw);
+    *reinterpret_cast<float4*>(img + B_TILE_BYTES + o) = make_float4(vb[i].x - hx, vb[i].y - hy, vb[i].z - hz, vb[i].w - hw);
+  }
+}
+
+template <bool A_MN, bool B_MN, int NB32, bool B_PRE>
 __global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_tc_kernel(const __grid_constant__ GemmArgs g) {
   constexpr int BN = NB32 * 32;
   constexpr int B_TILE_BYTES = BN * BK * 4;
@@ -61,7 +88,7 @@ __global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_
   constexpr int B_F4 = BN * BK / 4 / GROUP_THREADS;   // 2 * NB32
 
   extern __shared__ uint8_t smem_raw[];
-  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES, MMA_WARP);
+  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES, MMA_WARP, GROUP_THREADS + (B_PRE ? 1 : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_mn = g.m_tiles * g.n_tiles;
   const int total_tiles = tiles_mn * g.splits;
@@ -73,36 +100,78 @@ __global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_
     TileMap<A_MN, BM> ma;
     TileMap<B_MN, BN> mb;
     ma.init(ptid), mb.init(ptid);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % g.n_tiles, r = tile / g.n_tiles, mt = r % g.m_tiles, sp = r / g.m_tiles;
-      const int kb0 = sp * g.kb_per_split, kb1 = min(g.kb_total, kb0 + g.kb_per_split);
-      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        if ((int)(it % groups) != grp) continue;
-        const uint32_t stage = it % stages, ph = (it / stages) & 1u;
-        float4 va[A_F4], vb[B_F4];
-        load_tile<A_MN, BM, A_F4>(va, ma, g.A, g.lda, mt * BM, g.Mc, kb * BK, g.Kr);
-        load_tile<B_MN, BN, B_F4>(vb, mb, g.B, g.ldb, nt * BN, g.Nc, kb * BK, g.Kr);
-        if (A_MN) {   // bias gradient: a thread always holds the same four rows of A (TileMap<true, 128>)
-#pragma unroll
-          for (int i = 0; i < A_F4; ++i) cs.x += va[i].x, cs.y += va[i].y, cs.z += va[i].z, cs.w += va[i].w;
+    if (B_PRE) {
+      // (forward / input gradient: one split, kb in [0, kb_total)).  The group's K blocks are it = grp, grp + G, ...; the A
+      // chunks of the NEXT block are requested before the current block is split and stored, so the global round trip of
+      // block i+1 overlaps the shared-memory work of block i.
+      const int kbt = g.kb_total;
+      const long long total_blocks = (long long)((total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * kbt;   // of this CTA
+      auto coords = [&](long long blk, int& mt, int& nt, int& kb) {
+        const int tile = blockIdx.x + (int)(blk / kbt) * gridDim.x;
+        kb = (int)(blk % kbt), nt = tile % g.n_tiles, mt = (tile / g.n_tiles) % g.m_tiles;
+      };
+      float4 va[A_F4], vn[A_F4];
+      int mt, nt, kb;
+      long long blk = grp;
+      const int a_rows = (g.debug & 2) ? 0 : g.Mc;   // (ablation: every A chunk predicated off -> zeros)
+      if (blk < total_blocks) {
+        coords(blk, mt, nt, kb);
+        load_tile<A_MN, BM, A_F4>(va, ma, g.A, g.lda, mt * BM, a_rows, kb * BK, g.Kr);
+      }
+      for (; blk < total_blocks; blk += groups) {
+        const uint32_t it = (uint32_t)blk, stage = it % stages, ph = (it / stages) & 1u;
+        const int nt_cur = nt, kb_cur = kb;
+        if (blk + groups < total_blocks) {
+          coords(blk + groups, mt, nt, kb);
+          load_tile<A_MN, BM, A_F4>(vn, ma, g.A, g.lda, mt * BM, a_rows, kb * BK, g.Kr);
         }
         mbar_wait(c.empty_bar + 8 * stage, ph ^ 1u);
-        const uint32_t a_hi = c.smem_base + stage * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-        const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+        const uint32_t a_hi = c.smem_base + stage * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES, b_hi = a_lo + A_TILE_BYTES;
+        if (ptid == 0) {
+          const char* src = reinterpret_cast<const char*>(g.Bpre) + ((size_t)nt_cur * kbt + kb_cur) * 2 * B_TILE_BYTES;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c.full_bar + 8 * stage), "r"(2 * B_TILE_BYTES) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(b_hi), "l"(src),
+                       "r"(2 * B_TILE_BYTES), "r"(c.full_bar + 8 * stage)
+                       : "memory");
+        }
         store_tile<A_MN, BM, A_F4>(va, ma, a_hi, a_lo);
-        store_tile<B_MN, BN, B_F4>(vb, mb, b_hi, b_lo);
         fence_async_smem();
         mbar_arrive(c.full_bar + 8 * stage);
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i) va[i] = vn[i];
       }
-      if (A_MN && g.colsum != nullptr && nt == 0) {
-        const int row = mt * BM + ma.row_t;
-        if (row < g.Mc) {   // Mc % 4 == 0
-          atomicAdd(g.colsum + row, cs.x);
-          atomicAdd(g.colsum + row + 1, cs.y);
-          atomicAdd(g.colsum + row + 2, cs.z);
-          atomicAdd(g.colsum + row + 3, cs.w);
+    } else {
+    uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % g.n_tiles, r = tile / g.n_tiles, mt = r % g.m_tiles, sp = r / g.m_tiles;
+        const int kb0 = sp * g.kb_per_split, kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          if ((int)(it % groups) != grp) continue;
+          const uint32_t stage = it % stages, ph = (it / stages) & 1u;
+          float4 va[A_F4], vb[B_F4];
+          load_tile<A_MN, BM, A_F4>(va, ma, g.A, g.lda, mt * BM, g.Mc, kb * BK, g.Kr);
+          load_tile<B_MN, BN, B_F4>(vb, mb, g.B, g.ldb, nt * BN, g.Nc, kb * BK, g.Kr);
+          if (A_MN) {   // bias gradient: a thread always holds the same four rows of A (TileMap<true, 128>)
+  #pragma unroll
+            for (int i = 0; i < A_F4; ++i) cs.x += va[i].x, cs.y += va[i].y, cs.z += va[i].z, cs.w += va[i].w;
+          }
+          mbar_wait(c.empty_bar + 8 * stage, ph ^ 1u);
+          const uint32_t a_hi = c.smem_base + stage * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+          store_tile<A_MN, BM, A_F4>(va, ma, a_hi, a_lo);
+          store_tile<B_MN, BN, B_F4>(vb, mb, b_hi, b_lo);
+          fence_async_smem();
+          mbar_arrive(c.full_bar + 8 * stage);
+        }
+        if (A_MN && g.colsum != nullptr && nt == 0) {
+          const int row = mt * BM + ma.row_t;
+          if (row < g.Mc) {   // Mc % 4 == 0
+            atomicAdd(g.colsum + row, cs.x);
+            atomicAdd(g.colsum + row + 1, cs.y);
+            atomicAdd(g.colsum + row + 2, cs.z);
+            atomicAdd(g.colsum + row + 3, cs.w);
+          }
         }
       }
     }
@@ -138,7 +207,7 @@ __global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_
         for (int rr = 0; rr < 8; ++rr) {
           const int row = rr * 4 + (lane >> 3), grow = row0 + row;
           const float4 v = *reinterpret_cast<const float4*>(stg + row * EPI_PITCH + cc);
-          if (grow < g.Mc && gcol < g.Nc) {   // Nc % 4 == 0
+          if (grow < g.Mc && gcol < g.Nc && !(g.debug & 1)) {   // Nc % 4 == 0
             float* dst = g.C + (long long)grow * g.ldc + gcol;
             if (g.atomic) {
               atomicAdd(dst, v.x), atomicAdd(dst + 1, v.y), atomicAdd(dst + 2, v.z), atomicAdd(dst + 3, v.w);
@@ -156,7 +225,7 @@ __global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_
   cta_teardown(c, MMA_WARP);
 }
 
-template <bool A_MN, bool B_MN, int NB32>
+template <bool A_MN, bool B_MN, int NB32, bool B_PRE>
 int launch_one(const GemmArgs& g, int sm_count, cudaStream_t st) {
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * NB32 * 32 * BK * 4;
   GemmArgs a = g;
@@ -165,28 +234,32 @@ int launch_one(const GemmArgs& g, int sm_count, cudaStream_t st) {
   const int smem = smem_bytes(a.stages, STAGE_BYTES);
   static bool configured = false;
   if (!configured) {
-    DD_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<A_MN, B_MN, NB32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    DD_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<A_MN, B_MN, NB32, B_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     configured = true;
+  }
+  if (B_PRE) {
+    linear_prep_b_kernel<B_MN, NB32><<<dim3(a.kb_total, a.n_tiles), GROUP_THREADS, 0, st>>>(a.B, a.ldb, a.Nc, a.Kr, a.kb_total, const_cast<float*>(a.Bpre));
+    dd::count_launches(1);
   }
   const int total = a.m_tiles * a.n_tiles * a.splits;
   const int grid = total < sm_count ? total : sm_count;
-  linear_tc_kernel<A_MN, B_MN, NB32><<<grid, cta_threads(linear_groups<NB32>()), smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
+  linear_tc_kernel<A_MN, B_MN, NB32, B_PRE><<<grid, cta_threads(linear_groups<NB32>()), smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
   dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool B_PRE>
 int launch_nb(const GemmArgs& g, int nb32, int sm_count, cudaStream_t st) {
   switch (nb32) {
-    case 1: return launch_one<A_MN, B_MN, 1>(g, sm_count, st);
-    case 2: return launch_one<A_MN, B_MN, 2>(g, sm_count, st);
-    case 3: return launch_one<A_MN, B_MN, 3>(g, sm_count, st);
-    case 4: return launch_one<A_MN, B_MN, 4>(g, sm_count, st);
-    case 5: return launch_one<A_MN, B_MN, 5>(g, sm_count, st);
-    case 6: return launch_one<A_MN, B_MN, 6>(g, sm_count, st);
-    case 7: return launch_one<A_MN, B_MN, 7>(g, sm_count, st);
-    default: return launch_one<A_MN, B_MN, 8>(g, sm_count, st);
+    case 1: return launch_one<A_MN, B_MN, 1, B_PRE>(g, sm_count, st);
+    case 2: return launch_one<A_MN, B_MN, 2, B_PRE>(g, sm_count, st);
+    case 3: return launch_one<A_MN, B_MN, 3, B_PRE>(g, sm_count, st);
+    case 4: return launch_one<A_MN, B_MN, 4, B_PRE>(g, sm_count, st);
+    case 5: return launch_one<A_MN, B_MN, 5, B_PRE>(g, sm_count, st);
+    case 6: return launch_one<A_MN, B_MN, 6, B_PRE>(g, sm_count, st);
+    case 7: return launch_one<A_MN, B_MN, 7, B_PRE>(g, sm_count, st);
+    default: return launch_one<A_MN, B_MN, 8, B_PRE>(g, sm_count, st);
   }
 }
 
@@ -200,8 +273,29 @@ static int device_sms() {
 }
 
 // mode 0: forward, 1: input gradient, 2: weight gradient (split reduction + atomics)
+// N tile = 32 * nb32 columns: the narrowest of the widths 192 / 224 / 256 that wastes the fewest padded columns (a
+// 192-wide tile measured 5-12 % faster than 224 / 256 at equal waste: lighter producers per K block); one tile when N <= 256
+static int pick_nb32(int Nc) {
+  static const int forced_nb32 = getenv("DD_LINEAR_MAX_NB32") ? atoi(getenv("DD_LINEAR_MAX_NB32")) : 0;
+  const int n32 = (Nc + 31) / 32;
+  int nb32 = 0, best_waste = 1 << 30;
+  for (int cap = forced_nb32 > 0 ? forced_nb32 : 6; cap <= (forced_nb32 > 0 ? forced_nb32 : 8); ++cap) {
+    const int tiles = (n32 + cap - 1) / cap, nb = (n32 + tiles - 1) / tiles;
+    const int waste = ((n32 + nb - 1) / nb) * nb - n32;
+    if (waste < best_waste) best_waste = waste, nb32 = nb;
+  }
+  return nb32;
+}
+
+// bytes of the pre-split B operand (weights) of a forward / input-gradient contraction with Nc output columns over Kr
+size_t presplit_bytes(int Nc, int Kr) {
+  const int nb32 = pick_nb32(Nc), n32 = (Nc + 31) / 32;
+  const size_t n_tiles = (n32 + nb32 - 1) / nb32, kb_total = (Kr + BK - 1) / BK;
+  return n_tiles * kb_total * 2 * (size_t)(nb32 * 32) * BK * 4;
+}
+
 int gemm(int mode, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int Mc, int Nc, int Kr,
-         const float* bias, float* colsum, cudaStream_t st) {
+         const float* bias, float* colsum, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   DD_REQUIRE(Mc > 0 && Nc > 0 && Kr > 0, "linear: empty problem %d x %d x %d", Mc, Nc, Kr);
   // 16-byte accesses: along the reduction for K-major operands, along the rows for MN-major operands and for C
   DD_REQUIRE(Nc % 4 == 0 && (mode == 2 ? Mc % 4 == 0 : Kr % 4 == 0), "linear: feature dimensions must be multiples of 4 (got %d x %d over %d)", Mc, Nc, Kr);
@@ -213,16 +307,9 @@ int gemm(int mode, const float* A, long long lda, const float* B, long long ldb,
   memset(&g, 0, sizeof(g));
   g.A = A, g.B = B, g.C = C, g.bias = bias, g.colsum = colsum;
   g.lda = lda, g.ldb = ldb, g.ldc = ldc, g.Mc = Mc, g.Nc = Nc, g.Kr = Kr;
-  // N tile = 32 * nb32 columns: the narrowest of the widths 192 / 224 / 256 that wastes the fewest padded columns (a
-  // 192-wide tile measured 5-12 % faster than 224 / 256 at equal waste: lighter producers per K block); one tile when N <= 256
-  static const int forced_nb32 = getenv("DD_LINEAR_MAX_NB32") ? atoi(getenv("DD_LINEAR_MAX_NB32")) : 0;
-  const int n32 = (Nc + 31) / 32;
-  int nb32 = 0, best_waste = 1 << 30;
-  for (int cap = forced_nb32 > 0 ? forced_nb32 : 6; cap <= (forced_nb32 > 0 ? forced_nb32 : 8); ++cap) {
-    const int tiles = (n32 + cap - 1) / cap, nb = (n32 + tiles - 1) / tiles;
-    const int waste = ((n32 + nb - 1) / nb) * nb - n32;
-    if (waste < best_waste) best_waste = waste, nb32 = nb;
-  }
+  static const int debug = getenv("DD_LINEAR_DEBUG") ? atoi(getenv("DD_LINEAR_DEBUG")) : 0;
+  g.debug = debug;
+  const int nb32 = pick_nb32(Nc), n32 = (Nc + 31) / 32;
   g.n_tiles = (n32 + nb32 - 1) / nb32;
   g.m_tiles = (Mc + BM - 1) / BM;
   g.kb_total = (Kr + BK - 1) / BK;
@@ -236,9 +323,18 @@ int gemm(int mode, const float* A, long long lda, const float* B, long long ldb,
     g.splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
     g.atomic = 1;
   }
-  if (mode == 0) return launch_nb<false, false>(g, nb32, sms, st);
-  if (mode == 1) return launch_nb<false, true>(g, nb32, sms, st);
-  return launch_nb<true, true>(g, nb32, sms, st);
+  if (mode != 2) {   // the weight operand is split once per call into the workspace
+    const size_t need = presplit_bytes(Nc, Kr);
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("linear: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return DD_ERR_WORKSPACE;
+    }
+    DD_REQUIRE(((uintptr_t)workspace & 15) == 0, "linear: workspace must be 16-byte aligned");
+    g.Bpre = reinterpret_cast<const float*>(workspace);
+  }
+  if (mode == 0) return launch_nb<false, false, true>(g, nb32, sms, st);
+  if (mode == 1) return launch_nb<false, true, true>(g, nb32, sms, st);
+  return launch_nb<true, true, false>(g, nb32, sms, st);
 }
 
 }  // namespace tc
@@ -246,26 +342,34 @@ int gemm(int mode, const float* A, long long lda, const float* B, long long ldb,
 
 extern "C" {
 
-int dd_linear_fwd(const float* x, const float* w, const float* bias, int M, int K, int N, float* y, void* stream) {
+size_t dd_linear_workspace_bytes(int M, int K, int N) {
+  (void)M;
+  if (K <= 0 || N <= 0) return 0;
+  const size_t f = dd::tc::presplit_bytes(N, K), d = dd::tc::presplit_bytes(K, N);   // forward: N columns over K; input gradient: K columns over N
+  return f > d ? f : d;
+}
+
+int dd_linear_fwd(const float* x, const float* w, const float* bias, int M, int K, int N, float* y, void* workspace, size_t workspace_bytes,
+                  void* stream) {
   DD_REQUIRE(x && w && y, "dd_linear_fwd: NULL pointer");
-  return dd::tc::gemm(0, x, K, w, K, y, N, M, N, K, bias, nullptr, (cudaStream_t)stream);
+  return dd::tc::gemm(0, x, K, w, K, y, N, M, N, K, bias, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int dd_linear_bwd(const float* x, const float* w, const float* grad_y, int M, int K, int N, float* grad_x, float* grad_w,
-                  float* grad_b, void* stream) {
+                  float* grad_b, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DD_REQUIRE(grad_y != nullptr, "dd_linear_bwd: grad_y is NULL");
   DD_REQUIRE(!(grad_b != nullptr && grad_w == nullptr), "dd_linear_bwd: grad_b is produced by the weight-gradient pass (grad_w must be given)");
   if (grad_x) {
     DD_REQUIRE(w != nullptr, "dd_linear_bwd: w is NULL");
-    const int rc = dd::tc::gemm(1, grad_y, N, w, K, grad_x, K, M, K, N, nullptr, nullptr, st);
+    const int rc = dd::tc::gemm(1, grad_y, N, w, K, grad_x, K, M, K, N, nullptr, nullptr, workspace, workspace_bytes, st);
     if (rc != DD_OK) return rc;
   }
   if (grad_w) {
     DD_REQUIRE(x != nullptr, "dd_linear_bwd: x is NULL");
     DD_CHECK_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)N * K * sizeof(float), st));
     if (grad_b) DD_CHECK_CUDA(cudaMemsetAsync(grad_b, 0, (size_t)N * sizeof(float), st));
-    const int rc = dd::tc::gemm(2, grad_y, N, x, K, grad_w, K, N, K, M, nullptr, grad_b, st);
+    const int rc = dd::tc::gemm(2, grad_y, N, x, K, grad_w, K, N, K, M, nullptr, grad_b, nullptr, 0, st);
     if (rc != DD_OK) return rc;
   }
   return DD_OK;

@@ -124,8 +124,9 @@ SIGNATURES = {
     "dd_nhwc_to_nchw": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_block_tail_fwd": (C.c_int, [FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
     "dd_block_tail_bwd": (C.c_int, [FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
-    "dd_linear_fwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP]),
-    "dd_linear_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP]),
+    "dd_linear_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dd_linear_fwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, C.c_size_t, FP]),
+    "dd_linear_bwd": (C.c_int, [FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP, C.c_size_t, FP]),
     "dd_layernorm_workspace_bytes": (C.c_size_t, [C.c_int]),
     "dd_layernorm_fwd": (C.c_int, [FP, C.c_longlong, C.c_int, FP, FP, C.c_float, FP, FP, FP, FP]),
     "dd_layernorm_bwd": (C.c_int, [FP, FP, C.c_longlong, C.c_int, FP, FP, FP, FP, FP, FP, FP, C.c_size_t, FP]),

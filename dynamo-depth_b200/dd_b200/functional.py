@@ -695,7 +695,9 @@ class _LinearFn(torch.autograd.Function):
         N = w.shape[0]
         y = torch.empty((M, N), device=x.device, dtype=torch.float32)
         with _timed("linear_fwd", meta=(2.0 * M * K * N, 4.0 * (M * K + N * K + M * N)), detail=True):
-            L.check(L.load().dd_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), M, K, N, L.ptr(y), _stream()), "dd_linear_fwd")
+            lib = L.load()
+            ws = _workspace(lib.dd_linear_workspace_bytes(M, K, N), x.device)
+            L.check(lib.dd_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), M, K, N, L.ptr(y), L.ptr(ws), ws.numel(), _stream()), "dd_linear_fwd")
         ctx.save_for_backward(x2, w)
         ctx.has_bias = bias is not None
         ctx.x_shape = x.shape
@@ -714,8 +716,10 @@ class _LinearFn(torch.autograd.Function):
         flops = 2.0 * M * K * N * (int(bool(need_x)) + int(gw is not None))
         nbytes = 4.0 * ((M * N + N * K + M * K) * int(bool(need_x)) + (M * N + M * K + N * K) * int(gw is not None))
         with _timed("linear_bwd", meta=(flops, nbytes), detail=True):
-            L.check(L.load().dd_linear_bwd(L.ptr(x2), L.ptr(w), L.ptr(g2), M, K, N, L.ptr(gx), L.ptr(gw), L.ptr(gb), _stream()),
-                    "dd_linear_bwd")
+            lib = L.load()
+            ws = _workspace(lib.dd_linear_workspace_bytes(M, K, N), g.device)
+            L.check(lib.dd_linear_bwd(L.ptr(x2), L.ptr(w), L.ptr(g2), M, K, N, L.ptr(gx), L.ptr(gw), L.ptr(gb), L.ptr(ws), ws.numel(),
+                                      _stream()), "dd_linear_bwd")
         return (gx.reshape(ctx.x_shape) if need_x else None), (gw if need_w else None), gb
 
 

@@ -266,10 +266,15 @@ int dd_ground_score(const float* points /* (B,3,H,W) */, const float* w /* (K,3)
  *   dd_linear_bwd: grad_x (M,K) = grad_y . w;  grad_w (N,K) = grad_y^T . x;  grad_b (N) = column sums of grad_y.
  *                  Each output may be NULL (grad_b needs grad_w: it is summed by the weight-gradient pass); all
  *                  are overwritten.
+ * Workspace (dd_linear_workspace_bytes(M, K, N) bytes, 16-byte aligned): the weight operand of the forward and
+ * input-gradient contractions is split once per call into the (hi, lo) shared-memory tile images the kernel's K blocks
+ * fetch with one bulk copy each.
  * ------------------------------------------------------------------------------------------ */
-int dd_linear_fwd(const float* x, const float* w, const float* bias, int M, int K, int N, float* y, void* stream);
+size_t dd_linear_workspace_bytes(int M, int K, int N);
+int dd_linear_fwd(const float* x, const float* w, const float* bias, int M, int K, int N, float* y, void* workspace, size_t workspace_bytes,
+                  void* stream);
 int dd_linear_bwd(const float* x, const float* w, const float* grad_y, int M, int K, int N, float* grad_x, float* grad_w,
-                  float* grad_b, void* stream);
+                  float* grad_b, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout glue of the Lite-Mono blocks (networks/depth_encoder.py:204-221 DilatedConv.forward, :252-279 LGFI.forward;
