@@ -1334,7 +1334,7 @@ static bool use_winograd(int ks, int cin, int cout) {
 static int run_core(ConvArgs& args, int ks, float* wt_buf, const float* w_oihw, int Cout_f, int Cin_f, bool transpose,
                     cudaStream_t st) {
   if (use_pw_small(ks, transpose ? args.Cin : args.Cout, args.Ho, args.Wo, args.vin.up0))   // motion-decoder 1x1 reductions
-    return transpose ? run_pw_small_dgrad(args, w_oihw, st) : run_pw_small_fwd(args, w_oihw, st);
+    return transpose ? run_pw_small_dgrad(args, wt_buf, w_oihw, st) : run_pw_small_fwd(args, wt_buf, w_oihw, st);
   if (use_tc4_conv(ks, args.Cin, args.Cout))  // tensor cores (3xTF32, fp32 accuracy): every 3x3 layer with more than 16 output channels
     return run_conv_tc4(args, wt_buf, w_oihw, Cout_f, Cin_f, transpose, device_sms(), st);
   if (use_winograd(ks, args.Cin, args.Cout)) {

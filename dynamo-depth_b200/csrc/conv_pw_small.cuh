@@ -23,29 +23,50 @@ __device__ __forceinline__ const float* pw_plane(const VirtIn& v, int b, int ci,
   return ci < v.C0 ? v.x0 + ((size_t)b * v.C0 + ci) * HW : v.x1 + ((size_t)b * v.C1 + (ci - v.C0)) * HW;
 }
 
-// a.wt = the layer's own OIHW weights [Cout][Cin]
-template <int CO>
+// a.wt = weight table [Cin][4] (output channels padded to four, conv_prep_weights_kernel): ONE 16-byte load per input channel
+// brings all output-channel weights.  SPLIT: the CTA's 8 warps share 128 pixels and split the input channels (many channels);
+// otherwise every warp owns its own 128 pixels and walks all channels (few channels: no cross-warp reduction).
+template <int CO, bool SPLIT>
 __global__ void __launch_bounds__(PW_THREADS) pw_small_fwd_kernel(const __grid_constant__ ConvArgs a) {
-  __shared__ float4 part[PW_GROUPS][CO][32];
+  __shared__ float4 part[SPLIT ? PW_GROUPS : 1][CO][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5, b = blockIdx.z;
   const size_t HW = (size_t)a.Ho * a.Wo;
   const int HW4 = (int)(HW >> 2);
-  const int q = blockIdx.x * 32 + lane;
+  const int q = SPLIT ? blockIdx.x * 32 + lane : (blockIdx.x * PW_GROUPS + grp) * 32 + lane;
   const bool live = q < HW4;
   float4 acc[CO];
 #pragma unroll
   for (int co = 0; co < CO; ++co) acc[co] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live) {
 #pragma unroll 4
-    for (int ci = grp; ci < a.Cin; ci += PW_GROUPS) {
+    for (int ci = SPLIT ? grp : 0; ci < a.Cin; ci += SPLIT ? PW_GROUPS : 1) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(pw_plane(a.vin, b, ci, HW)) + q);
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wt) + ci);
+      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
       for (int co = 0; co < CO; ++co) {
-        const float w = co < a.Cout ? __ldg(a.wt + (size_t)co * a.Cin + ci) : 0.f;
-        acc[co].x = fmaf(w, v.x, acc[co].x), acc[co].y = fmaf(w, v.y, acc[co].y);
-        acc[co].z = fmaf(w, v.z, acc[co].z), acc[co].w = fmaf(w, v.w, acc[co].w);
+        acc[co].x = fmaf(w[co], v.x, acc[co].x), acc[co].y = fmaf(w[co], v.y, acc[co].y);
+        acc[co].z = fmaf(w[co], v.z, acc[co].z), acc[co].w = fmaf(w[co], v.w, acc[co].w);
       }
     }
+  }
+  auto finish = [&](int co, int qq, float4 s) {
+    const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+    s = make_float4(apply_act(s.x + bv, a.act), apply_act(s.y + bv, a.act), apply_act(s.z + bv, a.act), apply_act(s.w + bv, a.act));
+    const size_t o = ((size_t)b * a.Cout + co) * HW + (size_t)qq * 4;
+    if (a.residual) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + o));
+      s.x += r.x, s.y += r.y, s.z += r.z, s.w += r.w;
+    }
+    *reinterpret_cast<float4*>(a.out + o) = s;
+  };
+  if (!SPLIT) {
+    if (live) {
+#pragma unroll
+      for (int co = 0; co < CO; ++co)
+        if (co < a.Cout) finish(co, q, acc[co]);
+    }
+    return;
   }
 #pragma unroll
   for (int co = 0; co < CO; ++co) part[grp][co][lane] = acc[co];
@@ -59,19 +80,12 @@ __global__ void __launch_bounds__(PW_THREADS) pw_small_fwd_kernel(const __grid_c
       const float4 p = part[g][co][l];
       s.x += p.x, s.y += p.y, s.z += p.z, s.w += p.w;
     }
-    const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
-    s = make_float4(apply_act(s.x + bv, a.act), apply_act(s.y + bv, a.act), apply_act(s.z + bv, a.act), apply_act(s.w + bv, a.act));
-    const size_t o = ((size_t)b * a.Cout + co) * HW + (size_t)qq * 4;
-    if (a.residual) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + o));
-      s.x += r.x, s.y += r.y, s.z += r.z, s.w += r.w;
-    }
-    *reinterpret_cast<float4*>(a.out + o) = s;
+    finish(co, qq, s);
   }
 }
 
-// Data gradient: a.vin.x0 = g (B, CO_real = a.Cin, HW); a.Cout = channels of the layer's input; a.wt = OIHW weights
-// [a.Cin][a.Cout]; channels < split go to a.out (split channels per image), the rest to a.out1; a NULL destination is skipped.
+// Data gradient: a.vin.x0 = g (B, CO_real = a.Cin, HW); a.Cout = channels of the layer's input; a.wt = the forward table
+// [a.Cout][4]; channels < split go to a.out (split channels per image), the rest to a.out1; a NULL destination is skipped.
 template <int CO>
 __global__ void __launch_bounds__(PW_THREADS) pw_small_dgrad_kernel(const __grid_constant__ ConvArgs a) {
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5, b = blockIdx.z;
@@ -87,11 +101,11 @@ __global__ void __launch_bounds__(PW_THREADS) pw_small_dgrad_kernel(const __grid
 #pragma unroll 4
   for (int ci = grp; ci < a.Cout; ci += PW_GROUPS) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.wt) + ci);
+    const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-    for (int co = 0; co < CO; ++co) {
-      const float w = co < a.Cin ? __ldg(a.wt + (size_t)co * a.Cout + ci) : 0.f;
-      s.x = fmaf(w, g[co].x, s.x), s.y = fmaf(w, g[co].y, s.y), s.z = fmaf(w, g[co].z, s.z), s.w = fmaf(w, g[co].w, s.w);
-    }
+    for (int co = 0; co < CO; ++co)
+      s.x = fmaf(w[co], g[co].x, s.x), s.y = fmaf(w[co], g[co].y, s.y), s.z = fmaf(w[co], g[co].z, s.z), s.w = fmaf(w[co], g[co].w, s.w);
     float* dst = ci < split ? a.out : a.out1;
     if (dst == nullptr) continue;
     const size_t o = ci < split ? ((size_t)b * split + ci) * HW : ((size_t)b * (a.Cout - split) + (ci - split)) * HW;
@@ -171,21 +185,38 @@ static size_t pw_small_wgrad_bytes(int B, int H, int W, int Cin) {
   return (size_t)B * cpi * Cin * 4 * sizeof(float);
 }
 
-// forward: args as prepared by conv_fwd_impl (a.wt is set here to the raw weights)
-static int run_pw_small_fwd(ConvArgs& a, const float* w_oihw, cudaStream_t st) {
-  a.wt = w_oihw;
+// weight table [Cin_f][4] of the layer (Cout_f <= 4 columns, zero padded) for both directions
+static void pw_small_table(const float* w_oihw, float* wt_buf, int Cout_f, int Cin_f, cudaStream_t st) {
+  const size_t wn = (size_t)Cin_f * 4;
+  conv_prep_weights_kernel<<<(int)((wn + 255) / 256), 256, 0, st>>>(w_oihw, wt_buf, Cout_f, Cin_f, 1, 4, 0);
+  dd::count_launches(1);
+}
+
+// forward: args as prepared by conv_fwd_impl
+static int run_pw_small_fwd(ConvArgs& a, float* wt_buf, const float* w_oihw, cudaStream_t st) {
+  pw_small_table(w_oihw, wt_buf, a.Cout, a.Cin, st);
+  a.wt = wt_buf;
   const int HW4 = (int)(((size_t)a.Ho * a.Wo) / 4);
-  const dim3 grid((HW4 + 31) / 32, 1, a.B);
-  if (a.Cout <= 1) pw_small_fwd_kernel<1><<<grid, PW_THREADS, 0, st>>>(a);
-  else if (a.Cout <= 2) pw_small_fwd_kernel<2><<<grid, PW_THREADS, 0, st>>>(a);
-  else pw_small_fwd_kernel<4><<<grid, PW_THREADS, 0, st>>>(a);
+  const bool split = a.Cin > 32;
+  const dim3 grid(split ? (HW4 + 31) / 32 : (HW4 + PW_THREADS - 1) / PW_THREADS, 1, a.B);
+#define DD_PW_FWD(CO)                                                                  \
+  do {                                                                                 \
+    if (split) pw_small_fwd_kernel<CO, true><<<grid, PW_THREADS, 0, st>>>(a);          \
+    else pw_small_fwd_kernel<CO, false><<<grid, PW_THREADS, 0, st>>>(a);               \
+  } while (0)
+  if (a.Cout <= 1) DD_PW_FWD(1);
+  else if (a.Cout <= 2) DD_PW_FWD(2);
+  else DD_PW_FWD(4);
+#undef DD_PW_FWD
   dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
 
-static int run_pw_small_dgrad(ConvArgs& a, const float* w_oihw, cudaStream_t st) {
-  a.wt = w_oihw;
+// data gradient: a.Cin = the layer's output channels (<= 4), a.Cout = its input channels
+static int run_pw_small_dgrad(ConvArgs& a, float* wt_buf, const float* w_oihw, cudaStream_t st) {
+  pw_small_table(w_oihw, wt_buf, a.Cin, a.Cout, st);
+  a.wt = wt_buf;
   const int HW4 = (int)(((size_t)a.Ho * a.Wo) / 4);
   const dim3 grid((HW4 + 31) / 32, 1, a.B);
   if (a.Cin <= 1) pw_small_dgrad_kernel<1><<<grid, PW_THREADS, 0, st>>>(a);
