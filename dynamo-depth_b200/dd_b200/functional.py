@@ -937,7 +937,7 @@ def _nhwc_ptr(t):
     if not t.is_cuda:
         raise L.DynamoB200Error("dynamo_b200 ops need CUDA tensors (no CPU fallback)")
     if t.dtype != torch.float32 or t.dim() != 4 or not t.is_contiguous(memory_format=torch.channels_last):
-        raise L.DynamoB200Error("maxpool3x3s2: expected a channels_last fp32 (B,C,H,W) tensor")
+        raise L.DynamoB200Error("expected a channels_last fp32 (B,C,H,W) tensor")
     return t.data_ptr()
 
 
@@ -968,3 +968,36 @@ class _MaxPoolNHWCFn(torch.autograd.Function):
 def maxpool3x3s2(x):
     """F.max_pool2d(x, 3, 2, 1) on a channels_last CUDA tensor (C % 4 == 0); the result is channels_last as well."""
     return _MaxPoolNHWCFn.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# channels_last (ResNet trunks) -> NCHW (decoders) hand-over
+# ---------------------------------------------------------------------------------------------
+class _ToNCHWFn(torch.autograd.Function):
+    """A channels_last (B,C,H,W) activation as an NCHW-contiguous tensor, and its gradient back in channels_last, each as one
+    tiled transpose (dd_nhwc_to_nchw / dd_nchw_to_nhwc) instead of ATen's generic strided copy -- once per feature map, not
+    once per consumer."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, C_, H, W = x.shape
+        out = torch.empty((B, C_, H, W), device=x.device, dtype=torch.float32)
+        L.check(L.load().dd_nhwc_to_nchw(_nhwc_ptr(x), B, C_, H * W, L.ptr(out), _stream()), "dd_nhwc_to_nchw")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _prep(g)
+        B, C_, H, W = g.shape
+        gx = torch.empty((B, C_, H, W), device=g.device, dtype=torch.float32, memory_format=torch.channels_last)
+        L.check(L.load().dd_nchw_to_nhwc(L.ptr(g), B, C_, H * W, _nhwc_ptr(gx), _stream()), "dd_nchw_to_nhwc")
+        return gx
+
+
+def to_nchw(x):
+    """NCHW-contiguous view/copy of a 4-D CUDA fp32 tensor; tensors that already are NCHW-contiguous pass through."""
+    if x.dim() != 4 or x.is_contiguous() or not x.is_cuda or x.dtype != torch.float32:
+        return x
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        return x.contiguous()
+    return _ToNCHWFn.apply(x)

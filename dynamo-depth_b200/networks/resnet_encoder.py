@@ -79,4 +79,9 @@ class ResnetEncoder(nn.Module):
         for layer in (e.layer2, e.layer3, e.layer4):
             x = layer(x)
             self.features.append(x)
+        if self.channels_last and input_image.is_cuda:
+            # the decoders' kernels read NCHW: one tiled transpose per feature map here (and one for its gradient) instead of a
+            # generic strided copy inside every consumer
+            from dd_b200 import functional as DF
+            self.features = [DF.to_nchw(f) for f in self.features]
         return self.features
