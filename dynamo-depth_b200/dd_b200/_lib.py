@@ -135,6 +135,9 @@ SIGNATURES = {
     "dd_dwconv3x3_wgrad": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, C.c_size_t, FP]),
     "dd_maxpool3x3s2_nhwc_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, FP]),
     "dd_maxpool3x3s2_nhwc_bwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP]),
+    "dd_xca_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dd_xca_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP, FP, FP, C.c_size_t, FP]),
+    "dd_xca_bwd": (C.c_int, [FP, FP, FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, FP, C.c_size_t, FP]),
     "dd_bn_workspace_bytes": (C.c_size_t, [C.c_int]),
     "dd_bn_gelu_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, FP, FP, FP, FP, FP, FP,
                                  C.c_size_t, FP]),

@@ -1001,3 +1001,51 @@ def to_nchw(x):
     if not x.is_contiguous(memory_format=torch.channels_last):
         return x.contiguous()
     return _ToNCHWFn.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# cross-covariance attention core of the LGFI blocks (networks/depth_encoder.py:63-83, between qkv and proj)
+# ---------------------------------------------------------------------------------------------
+XCA_HEAD_DIMS = (8, 16, 28)
+
+
+class _XcaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, temperature, heads):
+        qkv, temp = _prep(qkv), _prep(temperature).reshape(-1)
+        B, N, C3 = qkv.shape
+        C_ = C3 // 3
+        D = C_ // heads
+        lib = L.load()
+        out = torch.empty((B, N, C_), device=qkv.device, dtype=torch.float32)
+        stats = torch.empty((2 * B * C_ * D + 2 * B * C_,), device=qkv.device, dtype=torch.float32)   # attn | scores | rq | rk
+        ws = _workspace(lib.dd_xca_workspace_bytes(B, N, C_, heads), qkv.device)
+        n1 = B * C_ * D
+        attn, scores, rq, rk = stats[:n1], stats[n1:2 * n1], stats[2 * n1:2 * n1 + B * C_], stats[2 * n1 + B * C_:]
+        L.check(lib.dd_xca_fwd(L.ptr(qkv), L.ptr(temp), B, N, C_, heads, L.ptr(out), L.ptr(attn), L.ptr(scores), L.ptr(rq), L.ptr(rk),
+                               L.ptr(ws), ws.numel(), _stream()), "dd_xca_fwd")
+        ctx.save_for_backward(qkv, temp, stats)
+        ctx.dims = (B, N, C_, heads, tuple(temperature.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, temp, stats = ctx.saved_tensors
+        B, N, C_, heads, tshape = ctx.dims
+        D = C_ // heads
+        g = _prep(g)
+        lib = L.load()
+        n1 = B * C_ * D
+        attn, scores, rq, rk = stats[:n1], stats[n1:2 * n1], stats[2 * n1:2 * n1 + B * C_], stats[2 * n1 + B * C_:]
+        gqkv = torch.empty_like(qkv)
+        gt_part = torch.empty((B, heads, D), device=g.device, dtype=torch.float32)
+        ws = _workspace(lib.dd_xca_workspace_bytes(B, N, C_, heads), g.device)
+        L.check(lib.dd_xca_bwd(L.ptr(qkv), L.ptr(temp), L.ptr(g), L.ptr(attn), L.ptr(scores), L.ptr(rq), L.ptr(rk), B, N, C_, heads,
+                               L.ptr(gqkv), L.ptr(gt_part), L.ptr(ws), ws.numel(), _stream()), "dd_xca_bwd")
+        gtemp = gt_part.sum((0, 2)).reshape(tshape) if ctx.needs_input_grad[1] else None
+        return gqkv, gtemp, None
+
+
+def xca_core(qkv, temperature, heads):
+    """(softmax((q^ @ k^T) * temperature) @ v) of XCA.forward for the (B,N,3C) output of its qkv layer -> (B,N,C)."""
+    return _XcaFn.apply(qkv, temperature, heads)

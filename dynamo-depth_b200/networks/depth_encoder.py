@@ -149,6 +149,10 @@ class XCA(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
+        if x.is_cuda and EncoderLinear.mode != "torch" and not (self.training and self.attn_drop.p > 0) and C % 32 == 0 and C <= 256:
+            from dd_b200 import functional as DF
+            if C // self.num_heads in DF.XCA_HEAD_DIMS:   # streaming Gram / softmax / apply kernels (csrc/xca.cu)
+                return self.proj_drop(self.proj(DF.xca_core(self.qkv(x), self.temperature, self.num_heads)))
         qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 4, 1)   # (3,B,h,d,N)
         q, k, v = F.normalize(qkv[0], dim=-1), F.normalize(qkv[1], dim=-1), qkv[2]
         attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.temperature).softmax(dim=-1))

@@ -354,6 +354,24 @@ int dd_dwconv3x3_wgrad(const float* x, const float* grad_y, int B, int C, int H,
 int dd_maxpool3x3s2_nhwc_fwd(const float* x, int B, int H, int W, int C, float* y, unsigned char* argmax, void* stream);
 int dd_maxpool3x3s2_nhwc_bwd(const float* grad_y, const unsigned char* argmax, int B, int H, int W, int C, float* grad_x, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Cross-covariance attention core of the Lite-Mono LGFI blocks (csrc/xca.cu): networks/depth_encoder.py:63-83 `XCA.forward`
+ * between its qkv and proj linear layers.  qkv is the (B,N,3C) output of the qkv layer (q | k | v, each heads x d channels),
+ * temperature is (heads); d = C / heads in {8, 16, 28}, C a multiple of 32 and <= 256.
+ *   dd_xca_fwd : out (B,N,C) = (softmax_j((q^ k^T)[i][j] * temperature[head]) @ v) in token-major order, q^ / k^ = q / k
+ *                L2-normalised over the N tokens (F.normalize, eps 1e-12); attn, scores (B,C,d) and rq, rk (B,C) = the
+ *                attention rows, the normalised Gram rows and the reciprocal norms are kept for the backward pass
+ *   dd_xca_bwd : grad_qkv (B,N,3C) and grad_temp_part (B,C): the temperature gradient of head h is the sum of
+ *                grad_temp_part over the batch and the d channels of the head
+ * Workspace: dd_xca_workspace_bytes(B, N, C, heads) (per-chunk partial Gram rows + coefficient matrices; deterministic).
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_xca_workspace_bytes(int B, int N, int C, int heads);
+int dd_xca_fwd(const float* qkv, const float* temperature, int B, int N, int C, int heads, float* out, float* attn, float* scores, float* rq,
+               float* rk, void* workspace, size_t workspace_bytes, void* stream);
+int dd_xca_bwd(const float* qkv, const float* temperature, const float* grad_out, const float* attn, const float* scores, const float* rq,
+               const float* rk, int B, int N, int C, int heads, float* grad_qkv, float* grad_temp_part, void* workspace, size_t workspace_bytes,
+               void* stream);
+
 #ifdef __cplusplus
 }
 #endif
