@@ -273,7 +273,10 @@ class LGFI(nn.Module):
         else:
             t = x.reshape(B, C, H * W).permute(0, 2, 1)
         if self.pos_embd is not None:
-            t = t + self.pos_embd(B, H, W).reshape(B, -1, t.shape[1]).permute(0, 2, 1)
+            # the position code does not depend on the image: on the fused path it is evaluated for ONE image and broadcast over
+            # the batch (the reference builds B identical copies, networks/depth_encoder.py:257-259)
+            pb = 1 if fused else B
+            t = t + self.pos_embd(pb, H, W).reshape(pb, -1, t.shape[1]).permute(0, 2, 1)
         t = t + self.gamma_xca * self.xca(self.norm_xca(t))
         if fused:
             y = self.norm(t.reshape(B, H, W, C))
