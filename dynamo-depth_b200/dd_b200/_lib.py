@@ -138,6 +138,10 @@ SIGNATURES = {
     "dd_xca_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dd_xca_fwd": (C.c_int, [FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP, FP, FP, C.c_size_t, FP]),
     "dd_xca_bwd": (C.c_int, [FP, FP, FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, FP, FP, C.c_size_t, FP]),
+    "dd_bn_nhwc_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "dd_bn_act_nhwc_fwd": (C.c_int, [FP, FP, C.c_longlong, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, FP, FP, FP, FP, FP, FP,
+                                     C.c_size_t, FP]),
+    "dd_bn_act_nhwc_bwd": (C.c_int, [FP, FP, FP, C.c_longlong, C.c_int, FP, FP, FP, FP, C.c_int, FP, FP, FP, FP, FP, C.c_size_t, FP]),
     "dd_bn_workspace_bytes": (C.c_size_t, [C.c_int]),
     "dd_bn_gelu_fwd": (C.c_int, [FP, C.c_int, C.c_int, C.c_int, FP, FP, C.c_float, C.c_float, C.c_int, FP, FP, FP, FP, FP, FP,
                                  C.c_size_t, FP]),

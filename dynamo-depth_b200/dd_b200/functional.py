@@ -1049,3 +1049,73 @@ class _XcaFn(torch.autograd.Function):
 def xca_core(qkv, temperature, heads):
     """(softmax((q^ @ k^T) * temperature) @ v) of XCA.forward for the (B,N,3C) output of its qkv layer -> (B,N,C)."""
     return _XcaFn.apply(qkv, temperature, heads)
+
+
+# ---------------------------------------------------------------------------------------------
+# channels_last BatchNorm2d + residual + activation (ResNet BasicBlock pattern, Lite-Mono stem)
+# ---------------------------------------------------------------------------------------------
+BN_ACTS = {"none": 0, "relu": 1, "gelu": 2}
+
+
+def bn_nhwc_supported(C_):
+    return C_ % 4 == 0 and C_ // 4 <= 256 and 256 % (C_ // 4) == 0
+
+
+class _BnActNHWCFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, momentum, eps, act):
+        x = x.float().contiguous(memory_format=torch.channels_last) if x.is_cuda else x
+        if residual is not None:
+            residual = residual.float().contiguous(memory_format=torch.channels_last)
+        weight, bias = _prep(weight), _prep(bias)
+        B, C_, H, W = x.shape
+        lib = L.load()
+        y = torch.empty((B, C_, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        stats = torch.empty((2, C_), device=x.device, dtype=torch.float32)
+        ws = _workspace(lib.dd_bn_nhwc_workspace_bytes(C_), x.device)
+        L.check(lib.dd_bn_act_nhwc_fwd(_nhwc_ptr(x), _nhwc_ptr(residual) if residual is not None else None, B * H * W, C_, L.ptr(weight),
+                                       L.ptr(bias), float(eps), float(momentum), int(act), _nhwc_ptr(y), L.ptr(stats[0]), L.ptr(stats[1]),
+                                       L.ptr(running_mean), L.ptr(running_var), L.ptr(ws), ws.numel(), _stream()), "dd_bn_act_nhwc_fwd")
+        ctx.save_for_backward(x, y if act == 1 else None, weight, bias, stats)
+        ctx.act, ctx.has_res = int(act), residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, weight, bias, stats = ctx.saved_tensors
+        B, C_, H, W = x.shape
+        g = g.float().contiguous(memory_format=torch.channels_last)
+        lib = L.load()
+        need_x, need_r = ctx.needs_input_grad[0], ctx.has_res and ctx.needs_input_grad[1]
+        need_w = weight is not None and ctx.needs_input_grad[2]
+        need_b = bias is not None and ctx.needs_input_grad[3]
+        if not (need_x or need_r or need_w or need_b):
+            return (None,) * 9
+        gx = torch.empty_like(x) if need_x else None                      # (empty_like keeps channels_last)
+        gr = torch.empty_like(x) if need_r else None
+        gw = torch.empty_like(weight) if need_w else None
+        gb = torch.empty_like(bias) if need_b else None
+        ws = _workspace(lib.dd_bn_nhwc_workspace_bytes(C_), x.device)
+        L.check(lib.dd_bn_act_nhwc_bwd(_nhwc_ptr(x), _nhwc_ptr(y) if y is not None else None, _nhwc_ptr(g), B * H * W, C_, L.ptr(weight),
+                                       L.ptr(bias), L.ptr(stats[0]), L.ptr(stats[1]), ctx.act, _nhwc_ptr(gx) if gx is not None else None,
+                                       _nhwc_ptr(gr) if gr is not None else None, L.ptr(gw), L.ptr(gb), L.ptr(ws), ws.numel(), _stream()),
+                "dd_bn_act_nhwc_bwd")
+        return gx, gr, gw, gb, None, None, None, None, None
+
+
+def bn_act_nhwc(x, bn, act="none", residual=None):
+    """act(bn(x) + residual) for an nn.BatchNorm2d in training mode on a channels_last CUDA tensor (csrc/batchnorm_nhwc.cu);
+    running statistics / num_batches_tracked updated as nn.BatchNorm2d.forward does.  Eval mode and unsupported channel counts
+    take the torch formulation."""
+    if not bn.training or not bn.track_running_stats or x.dim() != 4 or not x.is_cuda or not bn_nhwc_supported(x.shape[1]):
+        y = bn(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if act == "relu" else (torch.nn.functional.gelu(y) if act == "gelu" else y)
+    momentum = bn.momentum
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return _BnActNHWCFn.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, 0.0 if momentum is None else momentum,
+                              bn.eps, BN_ACTS[act])

@@ -184,6 +184,9 @@ class Conv(nn.Module):
 
     def forward(self, x):
         x = self.conv(x)
+        if self.bn_act and _fused(x) and x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+            from dd_b200 import functional as DF   # channels_last stem: BN + GELU in NHWC (csrc/batchnorm_nhwc.cu)
+            return DF.bn_act_nhwc(x, self.bn_gelu.bn, "gelu")
         return self.bn_gelu(x) if self.bn_act else x
 
 
@@ -297,6 +300,7 @@ class AvgPool(nn.Module):
 
 
 class LiteMono(nn.Module):
+    stem_channels_last = True
     def __init__(self, in_chans=3, model="lite-mono-8m", global_block=[1, 1, 1], global_block_type=["LGFI", "LGFI", "LGFI"],
                  drop_path_rate=0.2, layer_scale_init_value=1e-6, expan_ratio=6, heads=[8, 8, 8],
                  use_pos_embd_xca=[True, False, False], pretrained=True, **kwargs):
@@ -365,7 +369,14 @@ class LiteMono(nn.Module):
     def forward_features(self, x):
         x = (x - 0.45) / 0.225
         pyramid = [pool(x) for pool in self.input_downsample]
-        x = self.stem2(torch.cat((self.downsample_layers[0](x), pyramid[0]), dim=1))
+        if _fused(x) and LiteMono.stem_channels_last:
+            # the three 3x3 stem convolutions and stem2 run channels_last: cuDNN's tensor-core kernels are NHWC, an NCHW stem pays
+            # a layout conversion of the 250 MB half-resolution maps in front of and behind every convolution
+            from dd_b200 import functional as DF
+            h = self.downsample_layers[0](x.contiguous(memory_format=torch.channels_last))
+            x = DF.to_nchw(self.stem2(torch.cat((h, pyramid[0].contiguous(memory_format=torch.channels_last)), dim=1)))
+        else:
+            x = self.stem2(torch.cat((self.downsample_layers[0](x), pyramid[0]), dim=1))
         features, carry = [], [x]
         for i in range(3):
             if i > 0:

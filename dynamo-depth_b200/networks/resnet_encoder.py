@@ -55,6 +55,9 @@ class ResnetEncoder(nn.Module):
     # NHWC activations + weights on CUDA: cuDNN then runs its native tensor-core kernels without the per-layer
     # NCHW<->NHWC conversions and with the faster NHWC batch-norm kernels (same arithmetic, ~7 % of the bs32 step).
     channels_last = True
+    # BN + ReLU (+ identity) of the BasicBlocks through dd_bn_act_nhwc_*: measured SLOWER than cuDNN's single-read NHWC batch
+    # norm + ATen's ReLU / add on the B200 (bs32 step 114.5 -> 117.0 ms), so opt-in only (tests exercise it)
+    fused_blocks = False
 
     def to_channels_last(self):
         """Convert the trunk's weights once.  Must happen BEFORE a gradient arena / optimiser is built over the parameters:
@@ -63,25 +66,43 @@ class ResnetEncoder(nn.Module):
             self.encoder.to(memory_format=torch.channels_last)
             self._cl_ready = True
 
+    @staticmethod
+    def _basic_block(blk, x):
+        """torchvision BasicBlock.forward with BN + ReLU and BN + identity + ReLU as fused channels_last kernels
+        (dd_bn_act_nhwc_*; eval mode and exotic channel counts fall back to the torch ops inside bn_act_nhwc)."""
+        from dd_b200 import functional as DF
+        out = DF.bn_act_nhwc(blk.conv1(x), blk.bn1, "relu")
+        identity = x if blk.downsample is None else DF.bn_act_nhwc(blk.downsample[0](x), blk.downsample[1], "none")
+        return DF.bn_act_nhwc(blk.conv2(out), blk.bn2, "relu", residual=identity)
+
+    def _run_layer(self, layer, x, fused):
+        for blk in layer:
+            plain_ds = blk.downsample is None or (len(blk.downsample) == 2 and isinstance(blk.downsample[1], nn.BatchNorm2d))
+            x = self._basic_block(blk, x) if (fused and isinstance(blk, tvm.resnet.BasicBlock) and plain_ds) else blk(x)
+        return x
+
     def forward(self, input_image):
         e = self.encoder
-        if self.channels_last and input_image.is_cuda:
+        cl = self.channels_last and input_image.is_cuda
+        fused = cl and self.fused_blocks
+        if cl:
+            from dd_b200 import functional as DF
             self.to_channels_last()
             input_image = input_image.contiguous(memory_format=torch.channels_last)
-        x = e.relu(e.bn1(e.conv1((input_image - 0.45) / 0.225)))
+        x = e.conv1((input_image - 0.45) / 0.225)
+        x = DF.bn_act_nhwc(x, e.bn1, "relu") if fused else e.relu(e.bn1(x))
         self.features = [x]
-        if self.channels_last and x.is_cuda and x.shape[1] % 4 == 0 and (e.maxpool.kernel_size, e.maxpool.stride, e.maxpool.padding) == (3, 2, 1):
-            from dd_b200 import functional as DF   # gather-style NHWC max-pool (csrc/pool.cu)
-            x = e.layer1(DF.maxpool3x3s2(x))
+        if cl and x.shape[1] % 4 == 0 and (e.maxpool.kernel_size, e.maxpool.stride, e.maxpool.padding) == (3, 2, 1):
+            x = DF.maxpool3x3s2(x)   # gather-style NHWC max-pool (csrc/pool.cu)
         else:
-            x = e.layer1(e.maxpool(x))
+            x = e.maxpool(x)
+        x = self._run_layer(e.layer1, x, fused)
         self.features.append(x)
         for layer in (e.layer2, e.layer3, e.layer4):
-            x = layer(x)
+            x = self._run_layer(layer, x, fused)
             self.features.append(x)
-        if self.channels_last and input_image.is_cuda:
+        if cl:
             # the decoders' kernels read NCHW: one tiled transpose per feature map here (and one for its gradient) instead of a
             # generic strided copy inside every consumer
-            from dd_b200 import functional as DF
             self.features = [DF.to_nchw(f) for f in self.features]
         return self.features

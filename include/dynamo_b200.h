@@ -372,6 +372,26 @@ int dd_xca_bwd(const float* qkv, const float* temperature, const float* grad_out
                const float* rk, int B, int N, int C, int heads, float* grad_qkv, float* grad_temp_part, void* workspace, size_t workspace_bytes,
                void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-mode BatchNorm2d + residual add + activation on channels_last activations (csrc/batchnorm_nhwc.cu): the
+ * conv-bn-relu / conv-bn-(+identity)-relu pattern of the ResNet trunks (torchvision BasicBlock as used by
+ * networks/resnet_encoder.py:16-20,:125-134) and the Lite-Mono stem's BNGELU (networks/depth_encoder.py:113-122).
+ * x, residual, y, grad_* are (M = N*H*W, C) row-major (the memory of a channels_last tensor); C = 4 * a divisor of 256;
+ * act: 0 none, 1 ReLU, 2 exact GELU; gamma / beta / residual may be NULL.
+ *   dd_bn_act_nhwc_fwd : y = act((x - mean) * invstd * gamma + beta + residual) with batch statistics; save_mean / save_invstd
+ *                        (C) for the backward pass; running statistics (may be NULL) updated as nn.BatchNorm2d does
+ *   dd_bn_act_nhwc_bwd : grad_x, grad_residual (= grad_y * act'), grad_gamma, grad_beta (each may be NULL); y = the forward
+ *                        output (needed for act = ReLU only: its sign is the mask)
+ * Workspace: dd_bn_nhwc_workspace_bytes(C) (per-CTA partial sums; deterministic).
+ * ------------------------------------------------------------------------------------------ */
+size_t dd_bn_nhwc_workspace_bytes(int C);
+int dd_bn_act_nhwc_fwd(const float* x, const float* residual, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                       int act, float* y, float* save_mean, float* save_invstd, float* running_mean, float* running_var, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int dd_bn_act_nhwc_bwd(const float* x, const float* y, const float* grad_y, long long M, int C, const float* gamma, const float* beta,
+                       const float* save_mean, const float* save_invstd, int act, float* grad_x, float* grad_residual, float* grad_gamma,
+                       float* grad_beta, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
