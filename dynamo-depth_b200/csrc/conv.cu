@@ -466,6 +466,17 @@ __global__ void conv_route_kernel(const __grid_constant__ RouteArgs a) {
       } else if (a.up0 == DD_UP_NEAREST2) {
         s = folded(a, plane, 2 * y, 2 * x) + folded(a, plane, 2 * y, 2 * x + 1) + folded(a, plane, 2 * y + 1, 2 * x) +
             folded(a, plane, 2 * y + 1, 2 * x + 1);
+      } else if (2 * y - 1 >= 2 && 2 * y + 2 <= a.H - 3 && 2 * x - 1 >= 2 && 2 * x + 2 <= a.W - 3) {
+        // interior: none of the sixteen up-sampled positions that read this texel is a border, a reflection-fold row / column
+        // or clamped, so the transposed bilinear x2 weights are the constants (1/4, 3/4, 3/4, 1/4) per axis
+        const float* p0 = plane + (size_t)(2 * y - 1 + a.off) * a.Wp + (2 * x - 1 + a.off);
+        const float wgt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy) {
+          const float* pr = p0 + (size_t)dy * a.Wp;
+          const float row = 0.25f * __ldg(pr) + 0.75f * __ldg(pr + 1) + 0.75f * __ldg(pr + 2) + 0.25f * __ldg(pr + 3);
+          s = fmaf(wgt[dy], row, s);
+        }
       } else {
         for (int yy = 2 * y - 1; yy <= 2 * y + 2; ++yy) {
           if (yy < 0 || yy >= a.H) continue;
