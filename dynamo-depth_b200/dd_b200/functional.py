@@ -393,6 +393,8 @@ _WS_CACHE = {}
 
 def _workspace(nbytes, dev):
     """Per-device scratch buffer reused across calls (stream-ordered, so reuse on one stream is safe)."""
+    if dev.type != "cuda":
+        raise L.DynamoB200Error("dynamo_b200 ops need CUDA tensors (no CPU fallback)")
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
     buf = _WS_CACHE.get(key)
     if buf is None or buf.numel() < nbytes:

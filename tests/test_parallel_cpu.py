@@ -104,6 +104,21 @@ def test_cpu_tensors_are_refused_by_every_op():
         Fn.nchw_to_nhwc(x)
     with pytest.raises(DynamoB200Error):
         Fn.block_tail(x, x.permute(0, 2, 3, 1).contiguous(), torch.rand(3))
+    # round-2 encoder kernels: BatchNorm (+GELU), LayerNorm, depth-wise convolution, max-pool, XCA core
+    bn = torch.nn.BatchNorm2d(4).train()
+    x4 = torch.rand(2, 4, 8, 8)
+    with pytest.raises(DynamoB200Error):
+        Fn._BatchNormGeluFn.apply(x4, bn.weight, bn.bias, bn.running_mean, bn.running_var, 0.1, 1e-5, True)
+    with pytest.raises(DynamoB200Error):
+        Fn._BnActNHWCFn.apply(x4, None, bn.weight, bn.bias, bn.running_mean, bn.running_var, 0.1, 1e-5, 1)
+    with pytest.raises(DynamoB200Error):
+        Fn.layer_norm(torch.rand(4, 8), torch.ones(8), torch.zeros(8))
+    with pytest.raises(DynamoB200Error):
+        Fn.dwconv3x3(x4, torch.rand(4, 1, 3, 3), 1)
+    with pytest.raises(DynamoB200Error):
+        Fn.maxpool3x3s2(x4)
+    with pytest.raises(DynamoB200Error):
+        Fn.xca_core(torch.rand(1, 8, 96), torch.ones(4, 1, 1), 4)
 
 
 def test_encoder_layers_keep_the_reference_formulation_on_cpu():
