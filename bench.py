@@ -489,7 +489,7 @@ def run_ours(args):
             "config": {"workload": workload_name(cfg, args.phase), "name": args.config, "global_batch": world * BATCH,
                        "parallelism": f"dp{world}",
                        "l2": "per-step working set (colour frames plus GBs of activations) exceeds the 126 MB L2; no flush needed",
-                       "encoders": "PyTorch/cuDNN convolutions (TF32 = torch default, channels_last ResNets); Lite-Mono linear layers: hand-written tcgen05 3xTF32 kernel (fp32 accuracy, csrc/linear_tc.cu); decoders + loss path: hand-written kernels at fp32 accuracy",
+                       "encoders": "cuDNN convolutions (TF32 = torch default; channels_last ResNets and Lite-Mono stem); Lite-Mono linear layers: hand-written tcgen05 3xTF32 kernel (fp32 accuracy, csrc/linear_tc.cu); BatchNorm(+GELU), LayerNorm, depth-wise convolutions, XCA attention core, max-pool and layout glue of the encoders, all decoders and the loss path: hand-written kernels at fp32 accuracy",
                        "d_ground": "reference RANSAC prior kept on (host-driven torch ops, SURVEY 8f-1)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
