@@ -14,7 +14,14 @@
 // One thread per channel c = (head, i); a tile of 16 tokens is staged in shared memory by coalesced row loads and every
 // thread reads its own element plus the d elements of its head (broadcast).  Reductions over tokens go through per-CTA
 // partials and a fixed-order second stage: deterministic, no atomics.  qkv is read twice forward and 1 1/3 times backward.
-#include "dd_common.cuh"
+// Round 2b: the two token-streaming kernels that need only whole tiles of ONE matrix operand each (gram, apply) fetch their
+// 16-token x C tiles with tensor-map TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) into a two-stage ring: one elected thread issues
+// the box copies of tile i+1 while all threads compute on tile i (mbarrier complete_tx hand-over), so no thread spends issue
+// slots or registers on the staging loads.  DD_NO_TMA=1 (or a failed cuTensorMapEncodeTiled) selects the thread-staged kernels.
+#include <cuda.h>   // CUtensorMap + enums only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
+#include <stdlib.h>
+
+#include "tc_common.cuh"
 
 namespace dd {
 
@@ -244,6 +251,145 @@ __global__ void xca_bwd_apply_kernel(const float* __restrict__ qkv, const float*
   }
 }
 
+
+// ---- tensor-map TMA variants -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// same contract as xca_gram_kernel; a tile = box {C, XT} of map `ma` at column ax (and of `mb` at column bx), rows b * N + n
+template <int D>
+__global__ void xca_gram_tma_kernel(const __grid_constant__ CUtensorMap ma, int ax, const __grid_constant__ CUtensorMap mb, int bx, XcaTok g,
+                                    float* __restrict__ partial) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) unsigned long long bars[2];
+  const int c = threadIdx.x, h0 = (c / D) * D, b = blockIdx.y;
+  const int n0 = blockIdx.x * g.tokens_per_cta, n1 = min(g.N, n0 + g.tokens_per_cta);
+  const int tile = XT * g.C, ntiles = (n1 - n0 + XT - 1) / XT;
+  const uint32_t bar0 = tc::smem_u32(bars), sm0 = tc::smem_u32(sm);
+  if (c == 0) {
+    tc::mbar_init(bar0, 1), tc::mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int i) {
+    const uint32_t st = (uint32_t)(i & 1), bar = bar0 + 8 * st, dst = sm0 + st * 2u * tile * 4u;
+    const int y = b * g.N + n0 + i * XT;
+    tc::fence_async_smem();   // the stage's previous contents were read through the generic proxy
+    mbar_expect_tx(bar, 2u * tile * 4u);
+    tma_load_2d(dst, &ma, ax, y, bar);
+    tma_load_2d(dst + tile * 4u, &mb, bx, y, bar);
+  };
+  if (c == 0 && ntiles > 0) issue(0);
+  float G[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) G[j] = 0.f;
+  float na = 0.f, nb = 0.f;
+  for (int i = 0; i < ntiles; ++i) {
+    if (c == 0 && i + 1 < ntiles) issue(i + 1);   // (its stage was released by the barrier that closed iteration i - 1)
+    tc::mbar_wait(bar0 + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+    const float* as = sm + (i & 1) * 2 * tile;
+    const float* bs = as + tile;
+    const int tmax = min(XT, n1 - n0 - i * XT);   // rows past the chunk hold the next chunk's tokens (or zero fill): not summed
+#pragma unroll 2
+    for (int t = 0; t < tmax; ++t) {
+      const float ai = as[t * g.C + c], bc = bs[t * g.C + c];
+      na = fmaf(ai, ai, na), nb = fmaf(bc, bc, nb);
+      const float* bh = bs + t * g.C + h0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) G[j] = fmaf(ai, bh[j], G[j]);
+    }
+    __syncthreads();
+  }
+  float* p = partial + (((size_t)b * g.chunks + blockIdx.x) * g.C + c) * (D + 2);
+#pragma unroll
+  for (int j = 0; j < D; ++j) p[j] = G[j];
+  p[D] = na, p[D + 1] = nb;
+}
+
+// same contract as xca_apply_kernel; source tiles = box {C, XT} of map `ms` at column sx
+template <int D>
+__global__ void xca_apply_tma_kernel(const float* __restrict__ M, const __grid_constant__ CUtensorMap ms, int sx, float* __restrict__ dst,
+                                     long long dst_stride, XcaTok g) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) unsigned long long bars[2];
+  const int c = threadIdx.x, h0 = (c / D) * D, b = blockIdx.y;
+  const int n0 = blockIdx.x * g.tokens_per_cta, n1 = min(g.N, n0 + g.tokens_per_cta);
+  const int tile = XT * g.C, ntiles = (n1 - n0 + XT - 1) / XT;
+  const uint32_t bar0 = tc::smem_u32(bars), sm0 = tc::smem_u32(sm);
+  if (c == 0) {
+    tc::mbar_init(bar0, 1), tc::mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int i) {
+    const uint32_t st = (uint32_t)(i & 1), bar = bar0 + 8 * st;
+    tc::fence_async_smem();
+    mbar_expect_tx(bar, (uint32_t)tile * 4u);
+    tma_load_2d(sm0 + st * tile * 4u, &ms, sx, b * g.N + n0 + i * XT, bar);
+  };
+  if (c == 0 && ntiles > 0) issue(0);
+  float m[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) m[j] = __ldg(M + ((size_t)b * g.C + c) * D + j);
+  for (int i = 0; i < ntiles; ++i) {
+    if (c == 0 && i + 1 < ntiles) issue(i + 1);
+    tc::mbar_wait(bar0 + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+    const float* src = sm + (i & 1) * tile;
+    const int t0 = n0 + i * XT, tmax = min(XT, n1 - t0);
+#pragma unroll 2
+    for (int t = 0; t < tmax; ++t) {
+      const float* sh = src + t * g.C + h0;
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s = fmaf(m[j], sh[j], s);
+      dst[((long long)b * g.N + t0 + t) * dst_stride + c] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// 2-D fp32 tensor map over a row-major matrix (rows x cols, row stride in floats), box = box_cols x XT rows, zero fill outside
+static bool xca_make_map(CUtensorMap* map, const float* base, long long rows, int cols, long long row_stride, int box_cols) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (getenv("DD_NO_TMA") == nullptr && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+    (void)cudaGetLastError();
+  }
+  if (fn == nullptr) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_stride * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)XT};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int D>
+static int xca_tma_configure() {
+  static bool done = false;
+  if (!done) {
+    DD_CHECK_CUDA(cudaFuncSetAttribute(xca_gram_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * XT * 256 * (int)sizeof(float)));
+    DD_CHECK_CUDA(cudaFuncSetAttribute(xca_apply_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * XT * 256 * (int)sizeof(float)));
+    done = true;
+  }
+  return DD_OK;
+}
+static int xca_tma_configure(int D) { return D == 8 ? xca_tma_configure<8>() : (D == 16 ? xca_tma_configure<16>() : xca_tma_configure<28>()); }
+
 static int xca_tokens_per_cta(int B, int N) {
   // ~4 CTAs per SM over the batch, whole tiles, at most 256 tokens
   long long t = ((long long)B * N + 591) / 592;
@@ -306,9 +452,13 @@ int dd_xca_fwd(const float* qkv, const float* temperature, int B, int N, int C, 
   float* partial = reinterpret_cast<float*>(workspace);
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid(p.g.chunks, B);
-  DD_XCA_DISPATCH(D, xca_gram_kernel, <<<grid, C, 2 * XT * C * sizeof(float), st>>>(qkv, 3ll * C, qkv + C, 3ll * C, p.g, partial));
+  CUtensorMap mqkv;
+  const bool tma = (((uintptr_t)qkv & 15) == 0) && xca_make_map(&mqkv, qkv, (long long)B * N, 3 * C, 3ll * C, C) && xca_tma_configure(D) == DD_OK;
+  if (tma) DD_XCA_DISPATCH(D, xca_gram_tma_kernel, <<<grid, C, 4 * XT * C * sizeof(float), st>>>(mqkv, 0, mqkv, C, p.g, partial));
+  else DD_XCA_DISPATCH(D, xca_gram_kernel, <<<grid, C, 2 * XT * C * sizeof(float), st>>>(qkv, 3ll * C, qkv + C, 3ll * C, p.g, partial));
   DD_XCA_DISPATCH(D, xca_softmax_kernel, <<<B, C, C * sizeof(float), st>>>(partial, p.g.chunks, C, temperature, attn, scores, rq, rk));
-  DD_XCA_DISPATCH(D, xca_apply_kernel, <<<grid, C, XT * C * sizeof(float), st>>>(attn, qkv + 2 * C, 3ll * C, out, (long long)C, p.g));
+  if (tma) DD_XCA_DISPATCH(D, xca_apply_tma_kernel, <<<grid, C, 2 * XT * C * sizeof(float), st>>>(attn, mqkv, 2 * C, out, (long long)C, p.g));
+  else DD_XCA_DISPATCH(D, xca_apply_kernel, <<<grid, C, XT * C * sizeof(float), st>>>(attn, qkv + 2 * C, 3ll * C, out, (long long)C, p.g));
   count_launches(3);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
@@ -334,7 +484,11 @@ int dd_xca_bwd(const float* qkv, const float* temperature, const float* grad_out
   float* ck = cq + (size_t)B * C;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid(p.g.chunks, B);
-  DD_XCA_DISPATCH(D, xca_gram_kernel, <<<grid, C, 2 * XT * C * sizeof(float), st>>>(grad_out, (long long)C, qkv + 2 * C, 3ll * C, p.g, partial));
+  CUtensorMap mqkv, mg;
+  const bool tma = ((((uintptr_t)qkv | (uintptr_t)grad_out) & 15) == 0) && xca_make_map(&mqkv, qkv, (long long)B * N, 3 * C, 3ll * C, C) &&
+                   xca_make_map(&mg, grad_out, (long long)B * N, C, (long long)C, C) && xca_tma_configure(D) == DD_OK;
+  if (tma) DD_XCA_DISPATCH(D, xca_gram_tma_kernel, <<<grid, C, 4 * XT * C * sizeof(float), st>>>(mg, 0, mqkv, 2 * C, p.g, partial));
+  else DD_XCA_DISPATCH(D, xca_gram_kernel, <<<grid, C, 2 * XT * C * sizeof(float), st>>>(grad_out, (long long)C, qkv + 2 * C, 3ll * C, p.g, partial));
   DD_XCA_DISPATCH(D, xca_softmax_bwd_kernel, <<<B, C, (C + C * (D + 1)) * sizeof(float), st>>>(partial, p.g.chunks, C, temperature, attn, scores, rq,
                                                                                              rk, Mq, MqT, AT, cq, ck, grad_temp_part));
   DD_XCA_DISPATCH(D, xca_bwd_apply_kernel, <<<grid, C, 3 * XT * C * sizeof(float), st>>>(qkv, grad_out, Mq, MqT, AT, cq, ck, grad_qkv, p.g));
