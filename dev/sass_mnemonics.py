@@ -26,8 +26,8 @@ def main():
     demangled = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     print("SASS mnemonics per kernel of dynamo-depth_b200/dd_b200/libdynamo_b200.so (cuobjdump -sass; round 2, final build)")
     print("UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UBLKCP = cp.async.bulk, TLD4 = tex2Dgather, UTCBAR = tcgen05.commit, SYNCS = mbarrier, "
-          "LDGSTS = cp.async, FFMA2 = packed fp32 FMA; UTMALDG / UTMASTG (tensor-map TMA) do not occur: operands whose layout a tensor map "
-          "could describe are either split into hi / lo in registers first or fetched as pre-arranged images by UBLKCP")
+          "LDGSTS = cp.async, FFMA2 = packed fp32 FMA, UTMALDG = cp.async.bulk.tensor (tensor-map TMA: the token tiles of the XCA kernels); "
+          "the tensor-core kernels stage their operands through registers (hi / lo split) or as pre-arranged images by UBLKCP")
     print()
     seen = set()
     for (name, cnt), dem in zip(kernels.items(), demangled):

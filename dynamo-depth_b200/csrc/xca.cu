@@ -14,7 +14,7 @@
 // One thread per channel c = (head, i); a tile of 16 tokens is staged in shared memory by coalesced row loads and every
 // thread reads its own element plus the d elements of its head (broadcast).  Reductions over tokens go through per-CTA
 // partials and a fixed-order second stage: deterministic, no atomics.  qkv is read twice forward and 1 1/3 times backward.
-// Round 2b: the two token-streaming kernels that need only whole tiles of ONE matrix operand each (gram, apply) fetch their
+// Round 2b: the token-streaming kernels (gram, apply, backward apply) fetch their
 // 16-token x C tiles with tensor-map TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) into a two-stage ring: one elected thread issues
 // the box copies of tile i+1 while all threads compute on tile i (mbarrier complete_tx hand-over), so no thread spends issue
 // slots or registers on the staging loads.  DD_NO_TMA=1 (or a failed cuTensorMapEncodeTiled) selects the thread-staged kernels.
@@ -354,6 +354,64 @@ __global__ void xca_apply_tma_kernel(const float* __restrict__ M, const __grid_c
   }
 }
 
+// TMA variant of xca_bwd_apply_kernel: q / k tiles from the qkv map (columns 0 and C), grad_out tiles from its own map
+template <int D>
+__global__ void xca_bwd_apply_tma_kernel(const __grid_constant__ CUtensorMap mqkv, const __grid_constant__ CUtensorMap mg, const float* __restrict__ Mq,
+                                         const float* __restrict__ MqT, const float* __restrict__ AT, const float* __restrict__ cq,
+                                         const float* __restrict__ ck, float* __restrict__ gqkv, XcaTok g) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) unsigned long long bars[2];
+  const int c = threadIdx.x, h0 = (c / D) * D, b = blockIdx.y, C = g.C;
+  const int n0 = blockIdx.x * g.tokens_per_cta, n1 = min(g.N, n0 + g.tokens_per_cta);
+  const int tile = XT * C, ntiles = (n1 - n0 + XT - 1) / XT;
+  const uint32_t bar0 = tc::smem_u32(bars), sm0 = tc::smem_u32(sm);
+  if (c == 0) {
+    tc::mbar_init(bar0, 1), tc::mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int i) {
+    const uint32_t st = (uint32_t)(i & 1), bar = bar0 + 8 * st, dst = sm0 + st * 3u * tile * 4u;
+    const int y = b * g.N + n0 + i * XT;
+    tc::fence_async_smem();
+    mbar_expect_tx(bar, 3u * tile * 4u);
+    tma_load_2d(dst, &mqkv, 0, y, bar);
+    tma_load_2d(dst + tile * 4u, &mqkv, C, y, bar);
+    tma_load_2d(dst + 2u * tile * 4u, &mg, 0, y, bar);
+  };
+  if (c == 0 && ntiles > 0) issue(0);
+  float mq[D], mqt[D], at[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    mq[j] = __ldg(Mq + ((size_t)b * C + c) * D + j), mqt[j] = __ldg(MqT + ((size_t)b * C + c) * D + j);
+    at[j] = __ldg(AT + ((size_t)b * C + c) * D + j);
+  }
+  const float cqc = __ldg(cq + (size_t)b * C + c), ckc = __ldg(ck + (size_t)b * C + c);
+  for (int i = 0; i < ntiles; ++i) {
+    if (c == 0 && i + 1 < ntiles) issue(i + 1);
+    tc::mbar_wait(bar0 + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+    const float* qs = sm + (i & 1) * 3 * tile;
+    const float* ks = qs + tile;
+    const float* gs = ks + tile;
+    const int t0 = n0 + i * XT, tmax = min(XT, n1 - t0);
+    for (int t = 0; t < tmax; ++t) {
+      const float* qh = qs + t * C + h0;
+      const float* kh = ks + t * C + h0;
+      const float* gh = gs + t * C + h0;
+      float gq = -cqc * qs[t * C + c], gk = -ckc * ks[t * C + c], gv = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        gq = fmaf(mq[j], kh[j], gq);
+        gk = fmaf(mqt[j], qh[j], gk);
+        gv = fmaf(at[j], gh[j], gv);
+      }
+      float* orow = gqkv + ((long long)b * g.N + t0 + t) * 3 * C;
+      orow[c] = gq, orow[C + c] = gk, orow[2 * C + c] = gv;
+    }
+    __syncthreads();
+  }
+}
+
 // 2-D fp32 tensor map over a row-major matrix (rows x cols, row stride in floats), box = box_cols x XT rows, zero fill outside
 static bool xca_make_map(CUtensorMap* map, const float* base, long long rows, int cols, long long row_stride, int box_cols) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -384,6 +442,7 @@ static int xca_tma_configure() {
   if (!done) {
     DD_CHECK_CUDA(cudaFuncSetAttribute(xca_gram_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * XT * 256 * (int)sizeof(float)));
     DD_CHECK_CUDA(cudaFuncSetAttribute(xca_apply_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * XT * 256 * (int)sizeof(float)));
+    DD_CHECK_CUDA(cudaFuncSetAttribute(xca_bwd_apply_tma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * XT * 256 * (int)sizeof(float)));
     done = true;
   }
   return DD_OK;
@@ -491,7 +550,8 @@ int dd_xca_bwd(const float* qkv, const float* temperature, const float* grad_out
   else DD_XCA_DISPATCH(D, xca_gram_kernel, <<<grid, C, 2 * XT * C * sizeof(float), st>>>(grad_out, (long long)C, qkv + 2 * C, 3ll * C, p.g, partial));
   DD_XCA_DISPATCH(D, xca_softmax_bwd_kernel, <<<B, C, (C + C * (D + 1)) * sizeof(float), st>>>(partial, p.g.chunks, C, temperature, attn, scores, rq,
                                                                                              rk, Mq, MqT, AT, cq, ck, grad_temp_part));
-  DD_XCA_DISPATCH(D, xca_bwd_apply_kernel, <<<grid, C, 3 * XT * C * sizeof(float), st>>>(qkv, grad_out, Mq, MqT, AT, cq, ck, grad_qkv, p.g));
+  if (tma) DD_XCA_DISPATCH(D, xca_bwd_apply_tma_kernel, <<<grid, C, 6 * XT * C * sizeof(float), st>>>(mqkv, mg, Mq, MqT, AT, cq, ck, grad_qkv, p.g));
+  else DD_XCA_DISPATCH(D, xca_bwd_apply_kernel, <<<grid, C, 3 * XT * C * sizeof(float), st>>>(qkv, grad_out, Mq, MqT, AT, cq, ck, grad_qkv, p.g));
   count_launches(3);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
