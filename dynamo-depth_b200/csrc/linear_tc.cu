@@ -24,7 +24,7 @@
 //               registers -> (hi, lo) -> 128-byte-swizzled UMMA tiles in shared memory -> fence.proxy.async -> mbarrier `full`
 //   MMA warp    one thread issues tcgen05.mma (M = 128, N = BN <= 256, K = 8 per instruction, 12 per K block of 32),
 //               tcgen05.commit releases the stage (`empty`) and hands the accumulator to the epilogue (`tmem_full`)
-//   4 warps     epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> coalesced
+//   4 / 8 warps epilogue (8 for forward / input gradient: two per TMEM lane quarter on alternate column blocks): tcgen05.ld (32 lanes x 32 columns per warp) -> shared-memory transpose -> coalesced
 //               128-byte row segments (+ bias) or atomics; two accumulators in TMEM (2 x 256 columns) so the
 //               epilogue of tile i overlaps the MMAs of tile i+1
 #include <stdlib.h>
@@ -49,8 +49,11 @@ struct GemmArgs {
   int debug;             // DD_LINEAR_DEBUG ablations (timing experiments only): 1 = no global stores in the epilogue, 2 = no A loads
 };
 
-template <int NB32>
-__host__ __device__ constexpr int linear_groups() { return groups_for(stages_for(2 * A_TILE_BYTES + 2 * NB32 * 32 * BK * 4)); }
+// eight epilogue warps where the epilogue is heavy and the CTA has register room: forward / input gradient with tiles wider than 128
+// columns (two producer groups: 17 warps); narrow tiles (three producer groups) and the weight gradient keep four
+__host__ __device__ constexpr int linear_epi_warps(bool b_pre, int nb32) { return (b_pre && nb32 >= 5) ? 8 : 4; }
+template <int NB32, bool B_PRE>
+__host__ __device__ constexpr int linear_groups() { return groups_for(stages_for(2 * A_TILE_BYTES + 2 * NB32 * 32 * BK * 4, linear_epi_warps(B_PRE, NB32))); }
 
 // B operand of the forward / input-gradient contractions = the layer's weight: the same few tiles for every one of the
 // M / 128 row tiles.  Splitting them in the producers cost more instructions than the activations themselves (12 of the 20
@@ -78,17 +81,19 @@ __global__ void __launch_bounds__(GROUP_THREADS) linear_prep_b_kernel(const floa
 }
 
 template <bool A_MN, bool B_MN, int NB32, bool B_PRE>
-__global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_tc_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(cta_threads(linear_groups<NB32, B_PRE>(), linear_epi_warps(B_PRE, NB32)), 1)
+    linear_tc_kernel(const __grid_constant__ GemmArgs g) {
   constexpr int BN = NB32 * 32;
   constexpr int B_TILE_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  constexpr int G = linear_groups<NB32>();
-  constexpr int EPI_WARP0 = epi_warp0(G), MMA_WARP = mma_warp(G);
+  constexpr int G = linear_groups<NB32, B_PRE>();
+  constexpr int EW = linear_epi_warps(B_PRE, NB32);
+  constexpr int EPI_WARP0 = epi_warp0(G), MMA_WARP = mma_warp(G, EW);
   constexpr int A_F4 = BM * BK / 4 / GROUP_THREADS;   // 8
   constexpr int B_F4 = BN * BK / 4 / GROUP_THREADS;   // 2 * NB32
 
   extern __shared__ uint8_t smem_raw[];
-  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES, MMA_WARP, GROUP_THREADS + (B_PRE ? 1 : 0));
+  const Cta c = cta_setup(smem_raw, g.stages, STAGE_BYTES, MMA_WARP, GROUP_THREADS + (B_PRE ? 1 : 0), EW);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_mn = g.m_tiles * g.n_tiles;
   const int total_tiles = tiles_mn * g.splits;
@@ -179,8 +184,9 @@ __global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_
     mma_issue_loop<A_MN, B_MN, BN>(c, total_tiles, tiles_mn, g.kb_per_split, g.kb_total);
   } else {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - EPI_WARP0;   // == warp % 4: the TMEM lane quarter this warp may read
-    float* stg = c.epi_stage + ew * 32 * EPI_PITCH;
+    // warps with the same (warp & 3) = ew share TMEM lanes 32 ew .. 32 ew + 31 and take the 32-column blocks of their parity eh
+    const int ew = warp & 3, eh = (warp - EPI_WARP0) >> 2;
+    float* stg = c.epi_stage + (warp - EPI_WARP0) * 32 * EPI_PITCH;
     const uint32_t stg_addr = smem_u32(stg);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(cta_threads(linear_groups<NB32>()), 1) linear_
       tc_fence_after();
       const int row0 = mt * BM + ew * 32, col0 = nt * BN;
 #pragma unroll 1
-      for (int cb = 0; cb < NB32; ++cb) {
+      for (int cb = eh; cb < NB32; cb += EW / 4) {
         if (col0 + cb * 32 >= g.Nc) break;   // warp-uniform
         uint32_t r[32];
         tmem_ld32(c.tmem_base + ((uint32_t)(ew * 32) << 16) + buf * 256u + (uint32_t)(cb * 32), r);
@@ -229,9 +235,10 @@ template <bool A_MN, bool B_MN, int NB32, bool B_PRE>
 int launch_one(const GemmArgs& g, int sm_count, cudaStream_t st) {
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * NB32 * 32 * BK * 4;
   GemmArgs a = g;
-  a.stages = stages_for(STAGE_BYTES);
+  constexpr int EW = linear_epi_warps(B_PRE, NB32);
+  a.stages = stages_for(STAGE_BYTES, EW);
   // > half of the SM's shared memory in every configuration: one CTA per SM owns all 512 TMEM columns
-  const int smem = smem_bytes(a.stages, STAGE_BYTES);
+  const int smem = smem_bytes(a.stages, STAGE_BYTES, EW);
   static bool configured = false;
   if (!configured) {
     DD_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel<A_MN, B_MN, NB32, B_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
@@ -243,7 +250,7 @@ int launch_one(const GemmArgs& g, int sm_count, cudaStream_t st) {
   }
   const int total = a.m_tiles * a.n_tiles * a.splits;
   const int grid = total < sm_count ? total : sm_count;
-  linear_tc_kernel<A_MN, B_MN, NB32, B_PRE><<<grid, cta_threads(linear_groups<NB32>()), smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
+  linear_tc_kernel<A_MN, B_MN, NB32, B_PRE><<<grid, cta_threads(linear_groups<NB32, B_PRE>(), EW), smem < 120 * 1024 ? 120 * 1024 : smem, st>>>(a);
   dd::count_launches(1);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
@@ -279,7 +286,8 @@ static int pick_nb32(int Nc) {
   static const int forced_nb32 = getenv("DD_LINEAR_MAX_NB32") ? atoi(getenv("DD_LINEAR_MAX_NB32")) : 0;
   const int n32 = (Nc + 31) / 32;
   int nb32 = 0, best_waste = 1 << 30;
-  for (int cap = forced_nb32 > 0 ? forced_nb32 : 6; cap <= (forced_nb32 > 0 ? forced_nb32 : 8); ++cap) {
+  // (a 256-wide tile would leave a single stage next to the eight epilogue warps' staging buffers: widths up to 224)
+  for (int cap = forced_nb32 > 0 ? forced_nb32 : 6; cap <= (forced_nb32 > 0 ? forced_nb32 : 7); ++cap) {
     const int tiles = (n32 + cap - 1) / cap, nb = (n32 + tiles - 1) / tiles;
     const int waste = ((n32 + nb - 1) / nb) * nb - n32;
     if (waste < best_waste) best_waste = waste, nb32 = nb;

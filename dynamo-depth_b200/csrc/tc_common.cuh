@@ -23,11 +23,14 @@ constexpr int GROUP_THREADS = 128;       // one producer group
 // of shared memory -> two groups (13 warps, 128 registers per thread); narrower ones three (17 warps, 96 registers).
 __host__ __device__ constexpr int groups_for(int stages) { return stages >= 3 ? 3 : 2; }
 __host__ __device__ constexpr int epi_warp0(int groups) { return 4 * groups; }   // multiple of 4: epilogue warp w reads TMEM lane quarter w % 4
-__host__ __device__ constexpr int mma_warp(int groups) { return 4 * groups + 4; }
-__host__ __device__ constexpr int cta_threads(int groups) { return (4 * groups + 5) * 32; }
+// Epilogue warps ew = 4 or 8: with eight, two warps share a TMEM lane quarter and take alternate 32-column blocks -- the epilogue's
+// global stores were exposed with four (profiles/r02_linear_ablation.txt); the weight-gradient contraction and narrow tiles keep four
+// (the smaller register budget of a 21-warp CTA made those variants spill and run 10-30 % slower).
+__host__ __device__ constexpr int mma_warp(int groups, int ew) { return 4 * groups + ew; }
+__host__ __device__ constexpr int cta_threads(int groups, int ew) { return (4 * groups + ew + 1) * 32; }
 constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int EPI_PITCH = 36;            // floats; 16-byte aligned rows, conflict-free 128-bit accesses
-constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+__host__ __device__ constexpr int epi_bytes(int ew) { return ew * 32 * EPI_PITCH * 4; }
 constexpr int MAX_STAGES = 6;
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -177,27 +180,27 @@ struct Cta {
   int stages;
   uint32_t full_bar, empty_bar, tfull_bar, tempty_bar;
   uint32_t tmem_base;
-  float* epi_stage;        // 4 warps x 32 x EPI_PITCH floats
+  float* epi_stage;        // ew x 32 x EPI_PITCH floats
 };
 
-// dynamic shared memory: [<= 1023 B alignment slack][stages x STAGE_BYTES][EPI_BYTES][BAR_BYTES]
-__host__ __device__ constexpr int smem_bytes(int stages, int stage_bytes) { return 1024 + stages * stage_bytes + EPI_BYTES + BAR_BYTES; }
-__host__ __device__ constexpr int stages_for(int stage_bytes) {
-  return (SMEM_BUDGET - 1024 - EPI_BYTES - BAR_BYTES) / stage_bytes > MAX_STAGES ? MAX_STAGES
-                                                                                  : (SMEM_BUDGET - 1024 - EPI_BYTES - BAR_BYTES) / stage_bytes;
+// dynamic shared memory: [<= 1023 B alignment slack][stages x STAGE_BYTES][epi_bytes(ew)][BAR_BYTES]
+__host__ __device__ constexpr int smem_bytes(int stages, int stage_bytes, int ew) { return 1024 + stages * stage_bytes + epi_bytes(ew) + BAR_BYTES; }
+__host__ __device__ constexpr int stages_for(int stage_bytes, int ew) {
+  return (SMEM_BUDGET - 1024 - epi_bytes(ew) - BAR_BYTES) / stage_bytes > MAX_STAGES ? MAX_STAGES
+                                                                                      : (SMEM_BUDGET - 1024 - epi_bytes(ew) - BAR_BYTES) / stage_bytes;
 }
 
-__device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stage_bytes, int mma_warp_id, int full_count = GROUP_THREADS) {
+__device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stage_bytes, int mma_warp_id, int full_count, int ew) {
   Cta c;
   const uint32_t raw_addr = smem_u32(smem_raw);
   c.smem_base = (raw_addr + 1023u) & ~1023u;   // swizzle atoms are 1024-byte aligned
   c.smem = smem_raw + (c.smem_base - raw_addr);
   c.stages = stages;
   c.epi_stage = reinterpret_cast<float*>(c.smem + (size_t)stages * stage_bytes);
-  const uint32_t bar_base = c.smem_base + (uint32_t)(stages * stage_bytes) + EPI_BYTES;
+  const uint32_t bar_base = c.smem_base + (uint32_t)(stages * stage_bytes) + (uint32_t)epi_bytes(ew);
   c.full_bar = bar_base, c.empty_bar = bar_base + 8 * MAX_STAGES;
   c.tfull_bar = bar_base + 16 * MAX_STAGES, c.tempty_bar = c.tfull_bar + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(c.smem + (size_t)stages * stage_bytes + EPI_BYTES + 16 * MAX_STAGES + 32);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(c.smem + (size_t)stages * stage_bytes + epi_bytes(ew) + 16 * MAX_STAGES + 32);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -206,7 +209,7 @@ __device__ __forceinline__ Cta cta_setup(uint8_t* smem_raw, int stages, int stag
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(c.tfull_bar + 8 * b, 1);
-      mbar_init(c.tempty_bar + 8 * b, 4 * 32);
+      mbar_init(c.tempty_bar + 8 * b, ew * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
