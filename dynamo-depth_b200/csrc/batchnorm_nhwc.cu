@@ -92,23 +92,37 @@ __global__ void __launch_bounds__(BNH_THREADS) bnh_stats_kernel(const __grid_con
   bnh_reduce_store(a, s1, s2, red);
 }
 
-// partial[chunk][which][c] summed over the chunks: CTA = 32 channels x 8 chunk groups, fixed-order double sums
+// partial[chunk][which][c] summed over the chunks: CTA = 32 channels x 32 chunk groups (1024 threads), four independent loads per
+// step -- a first version with 8 groups and one load per step needed 74 dependent L2 round trips = 60 us for a 2-CTA kernel (ncu)
+constexpr int BNH_FIN_GROUPS = 32;
 __device__ __forceinline__ bool bnh_sum_partials(const BnhArgs& a, int c, double& S1, double& S2) {
-  __shared__ double sh[2][8][32];
+  __shared__ double sh[2][BNH_FIN_GROUPS][32];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   S1 = 0.0, S2 = 0.0;
-  if (c < a.C)
-    for (int k = grp; k < a.chunks; k += 8) S1 += (double)a.partial[((size_t)k * 2) * a.C + c], S2 += (double)a.partial[((size_t)k * 2 + 1) * a.C + c];
+  if (c < a.C) {
+    for (int k = grp; k < a.chunks; k += 4 * BNH_FIN_GROUPS) {
+      float v1[4], v2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = k + j * BNH_FIN_GROUPS;
+        const bool ok = kk < a.chunks;
+        v1[j] = ok ? a.partial[((size_t)kk * 2) * a.C + c] : 0.f;
+        v2[j] = ok ? a.partial[((size_t)kk * 2 + 1) * a.C + c] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) S1 += (double)v1[j], S2 += (double)v2[j];
+    }
+  }
   sh[0][grp][lane] = S1, sh[1][grp][lane] = S2;
   __syncthreads();
   if (grp != 0 || c >= a.C) return false;
-#pragma unroll
-  for (int g = 1; g < 8; ++g) S1 += sh[0][g][lane], S2 += sh[1][g][lane];
+#pragma unroll 8
+  for (int g = 1; g < BNH_FIN_GROUPS; ++g) S1 += sh[0][g][lane], S2 += sh[1][g][lane];
   return true;
 }
 
-// partials -> mean / invstd (+ running statistics); grid = ceil(C / 32), 256 threads
-__global__ void __launch_bounds__(256) bnh_finalize_kernel(const __grid_constant__ BnhArgs a) {
+// partials -> mean / invstd (+ running statistics); grid = ceil(C / 32), 1024 threads
+__global__ void __launch_bounds__(32 * BNH_FIN_GROUPS) bnh_finalize_kernel(const __grid_constant__ BnhArgs a) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double S1, S2;
   if (!bnh_sum_partials(a, c, S1, S2)) return;
@@ -201,7 +215,7 @@ __global__ void __launch_bounds__(BNH_THREADS) bnh_bwd_stats_kernel(const __grid
   bnh_reduce_store(a, s1, s2, red);
 }
 
-__global__ void __launch_bounds__(256) bnh_bwd_finalize_kernel(const __grid_constant__ BnhArgs a) {
+__global__ void __launch_bounds__(32 * BNH_FIN_GROUPS) bnh_bwd_finalize_kernel(const __grid_constant__ BnhArgs a) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double S1, S2;
   if (!bnh_sum_partials(a, c, S1, S2)) return;
@@ -292,7 +306,7 @@ int dd_bn_act_nhwc_fwd(const float* x, const float* residual, long long M, int C
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)2 * (BNH_THREADS / (C / 4)) * C * sizeof(float);   // 2 x RG x C floats = 8 KB
   bnh_stats_kernel<<<a.chunks, BNH_THREADS, smem, st>>>(a);
-  bnh_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(a);
+  bnh_finalize_kernel<<<(C + 31) / 32, 32 * BNH_FIN_GROUPS, 0, st>>>(a);
   bnh_apply_kernel<<<a.chunks, BNH_THREADS, 0, st>>>(a);
   count_launches(3);
   DD_CHECK_CUDA(cudaGetLastError());
@@ -322,7 +336,7 @@ int dd_bn_act_nhwc_bwd(const float* x, const float* y, const float* grad_y, long
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)2 * (BNH_THREADS / (C / 4)) * C * sizeof(float);
   bnh_bwd_stats_kernel<<<a.chunks, BNH_THREADS, smem, st>>>(a);
-  bnh_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(a);
+  bnh_bwd_finalize_kernel<<<(C + 31) / 32, 32 * BNH_FIN_GROUPS, 0, st>>>(a);
   count_launches(2);
   if (grad_x || grad_residual) {
     bnh_bwd_apply_kernel<<<a.chunks, BNH_THREADS, 0, st>>>(a);

@@ -152,19 +152,27 @@ __global__ void __launch_bounds__(LN_THREADS) layernorm_bwd_kernel(const __grid_
   }
 }
 
-// grad_gamma[c] = sum over CTAs of partial[cta][0][c], grad_beta likewise: CTA = 32 columns x 8 row groups, fixed-order double sums
-__global__ void __launch_bounds__(256) layernorm_reduce_kernel(const float* __restrict__ partial, int ctas, int C, float* __restrict__ ggamma,
-                                                               float* __restrict__ gbeta) {
-  __shared__ double sh[8][32];
+// grad_gamma[c] = sum over CTAs of partial[cta][0][c], grad_beta likewise: CTA = 32 columns x 32 row groups (1024 threads), four
+// independent loads per step (one load per step over 8 groups = 148 dependent L2 round trips = 63 us, ncu); fixed-order double sums
+__global__ void __launch_bounds__(1024) layernorm_reduce_kernel(const float* __restrict__ partial, int ctas, int C, float* __restrict__ ggamma,
+                                                                float* __restrict__ gbeta) {
+  __shared__ double sh[32][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
   double s = 0.0;
-  if (c < 2 * C)
-    for (int k = grp; k < ctas; k += 8) s += (double)partial[(size_t)k * 2 * C + c];
+  if (c < 2 * C) {
+    for (int k = grp; k < ctas; k += 4 * 32) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (k + 32 * j < ctas) ? partial[(size_t)(k + 32 * j) * 2 * C + c] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s += (double)v[j];
+    }
+  }
   sh[grp][threadIdx.x & 31] = s;
   __syncthreads();
   if (grp == 0 && c < 2 * C) {
-#pragma unroll
-    for (int g = 1; g < 8; ++g) s += sh[g][threadIdx.x];
+#pragma unroll 8
+    for (int g = 1; g < 32; ++g) s += sh[g][threadIdx.x];
     if (c < C) { if (ggamma) ggamma[c] = (float)s; }
     else if (gbeta) gbeta[c - C] = (float)s;
   }
@@ -239,7 +247,7 @@ int dd_layernorm_bwd(const float* x, const float* grad_y, long long M, int C, co
   DD_LN_DISPATCH(layernorm_bwd_kernel, <<<grid, LN_THREADS, smem, st>>>(a));
   count_launches(1);
   if (affine) {
-    layernorm_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(a.partial, grid, C, grad_gamma, grad_beta);
+    layernorm_reduce_kernel<<<(2 * C + 31) / 32, 1024, 0, st>>>(a.partial, grid, C, grad_gamma, grad_beta);
     count_launches(1);
   }
   DD_CHECK_CUDA(cudaGetLastError());

@@ -109,11 +109,15 @@ __global__ void xca_softmax_kernel(const float* __restrict__ partial, int chunks
   double G[D], na = 0.0, nb = 0.0;
 #pragma unroll
   for (int j = 0; j < D; ++j) G[j] = 0.0;
+#pragma unroll(D > 16 ? 2 : 4)   // several chunks' loads in flight (one chunk per L2 round trip made this tiny kernel 21 us)
   for (int k = 0; k < chunks; ++k) {
     const float* p = partial + (((size_t)b * chunks + k) * C + c) * (D + 2);
+    float v[D + 2];
 #pragma unroll
-    for (int j = 0; j < D; ++j) G[j] += (double)p[j];
-    na += (double)p[D], nb += (double)p[D + 1];
+    for (int j = 0; j < D + 2; ++j) v[j] = p[j];
+#pragma unroll
+    for (int j = 0; j < D; ++j) G[j] += (double)v[j];
+    na += (double)v[D], nb += (double)v[D + 1];
   }
   // F.normalize(dim=-1): x / max(||x||, 1e-12)
   const float rqc = 1.f / fmaxf((float)sqrt(na), 1e-12f), rkc = 1.f / fmaxf((float)sqrt(nb), 1e-12f);
@@ -150,10 +154,14 @@ __global__ void xca_softmax_bwd_kernel(const float* __restrict__ partial, int ch
   double gAd[D];
 #pragma unroll
   for (int j = 0; j < D; ++j) gAd[j] = 0.0;
+#pragma unroll(D > 16 ? 2 : 4)
   for (int k = 0; k < chunks; ++k) {
     const float* p = partial + (((size_t)b * chunks + k) * C + c) * (D + 2);
+    float v[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) gAd[j] += (double)p[j];
+    for (int j = 0; j < D; ++j) v[j] = p[j];
+#pragma unroll
+    for (int j = 0; j < D; ++j) gAd[j] += (double)v[j];
   }
   const float rqc = __ldg(rq + (size_t)b * C + c), rkc = __ldg(rk + (size_t)b * C + c);
   rk_s[c] = rkc;
