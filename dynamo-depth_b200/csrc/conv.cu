@@ -1410,8 +1410,7 @@ struct ConvWs {
   size_t fwd_bytes;   // what the forward pass needs (prepared weights + materialised up-sampling)
 };
 
-__global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int BC, int hi, int wi, int ho, int wo,
-                                  int sigmoid);
+static void launch_resize_fwd(const float* x, float* out, int BC, int hi, int wi, int ho, int wo, int sigmoid, cudaStream_t st);
 
 // Bilinear x2 up-sampling of x0 (depth_decoder.py:104) is materialised once per call into the workspace (a few tens of
 // MB, written and read once at HBM speed) so that the convolution loaders stay one tap per element; returns the
@@ -1420,10 +1419,7 @@ static VirtIn materialise_up(const dd_conv_desc* d, void* workspace, const ConvW
   VirtIn v = make_vin(d);
   if (d->up0 != DD_UP_BILINEAR2) return v;
   float* up = reinterpret_cast<float*>((char*)workspace + ws.up);
-  const size_t n = (size_t)d->B * d->C0 * d->H * d->W;
-  resize_fwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(d->x0, up, d->B * d->C0, d->H / 2, d->W / 2,
-                                                                                          d->H, d->W, 0);
-  dd::count_launches(1);
+  launch_resize_fwd(d->x0, up, d->B * d->C0, d->H / 2, d->W / 2, d->H, d->W, 0, st);
   v.x0 = up, v.H0 = d->H, v.W0 = d->W, v.up0 = DD_UP_NONE;
   return v;
 }
@@ -1643,6 +1639,58 @@ __global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+// Exact x2 up-sampling (every bilinear resize of the decoders: depth_decoder.py:104,:112-113, motion_decoder.py:38 from one level to
+// the next): thread = 2 output rows x 4 output columns from a 3 x 4 input neighbourhood (12 loads for 8 outputs instead of 32, one
+// 16-byte store per row).  Taps, weights and the order of operations are those of resize_taps / resize_fwd_kernel for scale 1/2
+// (src = dst / 2 - 1/4 clamped at 0), so the results are bit-identical to the generic kernel.
+__global__ void __launch_bounds__(256) resize2x_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int BC, int hi, int wi, int sigmoid) {
+  const int ho = 2 * hi, wo = 2 * wi, wq = wo >> 2;   // wq output quads per row (wi even)
+  const size_t n = (size_t)BC * hi * wq;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % wq), k = (int)((i / wq) % hi);
+    const size_t bc = i / ((size_t)wq * hi);
+    const float* p = x + bc * hi * wi;
+    // input rows k-1, k, k+1 and columns 2j-1 .. 2j+2 (clamped); v[r][c]
+    const int rows[3] = {max(k - 1, 0), k, min(k + 1, hi - 1)};
+    const int cols[4] = {max(2 * j - 1, 0), 2 * j, 2 * j + 1, min(2 * j + 2, wi - 1)};
+    float v[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[r][c] = __ldg(p + rows[r] * wi + cols[c]);
+    // per output column m of the quad: (index of tap 0, index of tap 1, weight of tap 1) into cols[]
+    int ca[4] = {0, 1, 1, 2}, cb[4] = {1, 2, 2, 3};
+    float lx[4] = {0.75f, 0.25f, 0.75f, 0.25f};
+    if (j == 0) ca[0] = 1, cb[0] = 2, lx[0] = 0.f;   // dst = 0: src clamps to 0 -> taps (0, 1), weight 0
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // output row 2k + half: taps (k-1, k; 3/4) or (k, k+1; 1/4); dst = 0: taps (0, 1), weight 0
+      int ra = half == 0 ? 0 : 1, rb = half == 0 ? 1 : 2;
+      float ly = half == 0 ? 0.75f : 0.25f;
+      if (half == 0 && k == 0) ra = 1, rb = 2, ly = 0.f;
+      float o[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float v00 = v[ra][ca[m]], v01 = v[ra][cb[m]], v10 = v[rb][ca[m]], v11 = v[rb][cb[m]];
+        o[m] = (1.f - ly) * ((1.f - lx[m]) * v00 + lx[m] * v01) + ly * ((1.f - lx[m]) * v10 + lx[m] * v11);
+        if (sigmoid) o[m] = 1.f / (1.f + expf(-o[m]));
+      }
+      *reinterpret_cast<float4*>(out + (bc * ho + 2 * k + half) * wo + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+static void launch_resize_fwd(const float* x, float* out, int BC, int hi, int wi, int ho, int wo, int sigmoid, cudaStream_t st) {
+  if (ho == 2 * hi && wo == 2 * wi && wi % 2 == 0 && wi >= 2 && hi >= 2 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const size_t n = (size_t)BC * hi * (wo / 4);
+    resize2x_fwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(x, out, BC, hi, wi, sigmoid);
+  } else {
+    const size_t n = (size_t)BC * ho * wo;
+    resize_fwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, st>>>(x, out, BC, hi, wi, ho, wo, sigmoid);
+  }
+  dd::count_launches(1);
+}
+
 __global__ void resize_bwd_kernel(const float* __restrict__ go, const float* __restrict__ out, float* __restrict__ gx, int BC,
                                   int hi, int wi, int ho, int wo, int sigmoid) {
   const size_t n = (size_t)BC * ho * wo;
@@ -1689,9 +1737,7 @@ int dd_resize_bilinear_fwd(const float* x, int BC, int h_in, int w_in, int h_out
                            void* stream) {
   using namespace dd;
   DD_REQUIRE(x && out && BC > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0, "dd_resize_bilinear_fwd: bad arguments");
-  const size_t n = (size_t)BC * h_out * w_out;
-  resize_fwd_kernel<<<(int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368), 256, 0, (cudaStream_t)stream>>>(
-      x, out, BC, h_in, w_in, h_out, w_out, sigmoid); dd::count_launches(1);
+  launch_resize_fwd(x, out, BC, h_in, w_in, h_out, w_out, sigmoid, (cudaStream_t)stream);
   DD_CHECK_CUDA(cudaGetLastError());
   return DD_OK;
 }
